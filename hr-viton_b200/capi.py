@@ -1,0 +1,67 @@
+"""ctypes binding of include/hrviton_sm100.h.  There is NO CPU fallback: if the shared library is missing
+or a call fails, this raises."""
+import ctypes
+import os
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG, "libhrviton_sm100.so")
+
+BF16, F32 = 0, 1
+ACT_NONE, ACT_RELU, ACT_LRELU, ACT_TANH = 0, 1, 2, 3
+NHWC, NCHW = 0, 1
+EPI_LINEAR, EPI_SPADE = 0, 1
+
+EXPORTS = ["hrv_conv2d_fwd", "hrv_instnorm_stats", "hrv_instnorm_apply", "hrv_nchw_to_nhwc", "hrv_nhwc_to_nchw",
+           "hrv_space_to_depth", "hrv_avgpool3s2", "hrv_bilinear_up2_add", "hrv_flow_warp", "hrv_last_error",
+           "hrv_version", "hrv_device_sm_count"]
+
+
+class Tensor(ctypes.Structure):
+    _fields_ = [("ptr", ctypes.c_void_p), ("n", ctypes.c_int32), ("h", ctypes.c_int32), ("w", ctypes.c_int32),
+                ("c", ctypes.c_int32), ("pitch", ctypes.c_int32), ("dtype", ctypes.c_int32)]
+
+
+class ConvParams(ctypes.Structure):
+    _fields_ = [("inp", Tensor), ("wpack", ctypes.c_void_p),
+                ("kh", ctypes.c_int32), ("kw", ctypes.c_int32), ("off_y", ctypes.c_int32), ("off_x", ctypes.c_int32),
+                ("bk", ctypes.c_int32), ("bn", ctypes.c_int32), ("n_gemm", ctypes.c_int32),
+                ("out", Tensor), ("out_layout", ctypes.c_int32), ("epi", ctypes.c_int32), ("act", ctypes.c_int32),
+                ("scale", ctypes.c_void_p), ("shift", ctypes.c_void_p),
+                ("res", Tensor), ("x0", Tensor), ("x1", Tensor), ("x0_shift", ctypes.c_int32),
+                ("mean", ctypes.c_void_p), ("rstd", ctypes.c_void_p), ("noise", ctypes.c_void_p),
+                ("noise_scale", ctypes.c_void_p)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("hrviton_b200: %s is missing — run `python __graft_entry__.py build` (no CPU fallback exists)" % LIB_PATH)
+    L = ctypes.CDLL(LIB_PATH)
+    L.hrv_last_error.restype = ctypes.c_char_p
+    vp, i32, f32 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_float
+    TP = ctypes.POINTER(Tensor)
+    L.hrv_conv2d_fwd.argtypes = [ctypes.POINTER(ConvParams), vp]
+    L.hrv_instnorm_stats.argtypes = [TP, i32, TP, i32, i32, vp, vp, f32, vp, vp, vp, ctypes.c_size_t, vp]
+    L.hrv_instnorm_apply.argtypes = [TP, vp, vp, i32, TP, vp]
+    L.hrv_nchw_to_nhwc.argtypes = [vp, i32, i32, i32, TP, vp]
+    L.hrv_nhwc_to_nchw.argtypes = [TP, vp, vp]
+    L.hrv_space_to_depth.argtypes = [TP, TP, vp]
+    L.hrv_avgpool3s2.argtypes = [TP, TP, vp]
+    L.hrv_bilinear_up2_add.argtypes = [TP, TP, TP, vp]
+    L.hrv_flow_warp.argtypes = [vp, vp, vp, TP, TP, vp, vp, vp]
+    for name in EXPORTS:
+        fn = getattr(L, name)
+        if name != "hrv_last_error":
+            fn.restype = ctypes.c_int
+    _lib = L
+    return L
+
+
+def check(rc, what):
+    if rc != 0:
+        raise RuntimeError("%s failed (%d): %s" % (what, rc, lib().hrv_last_error().decode()))

@@ -1,0 +1,444 @@
+// aux_kernels.cu — the HBM-bound kernels of the hot path (NHWC bf16, 16-byte vector accesses, 8 channels/thread):
+// InstanceNorm statistics (with the SPADE noise, virtual up-sampling and concat), InstanceNorm apply, layout
+// converters with nearest resampling, space-to-depth, 3x3/s2 average pool, bilinear x2 (+add), and the fused
+// appearance-flow warp.  Citations: see include/hrviton_sm100.h.
+#include "hrv_host.h"
+#include "hrv_ptx.cuh"
+
+namespace hrv {
+
+struct View {
+  const void* ptr;
+  int n, h, w, c, pitch, dtype;
+};
+static View mk(const hrv_tensor* t) {
+  View v;
+  if (t) { v.ptr = t->ptr; v.n = t->n; v.h = t->h; v.w = t->w; v.c = t->c; v.pitch = t->pitch; v.dtype = t->dtype; }
+  else { memset(&v, 0, sizeof(v)); }
+  return v;
+}
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
+  f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 o;
+  o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]); o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
+  return o;
+}
+__device__ __forceinline__ uint4 ldg16(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+
+// ------------------------------------------------------------------------------------------------ IN statistics
+// grid (chunks, N); thread = (pixel lane, channel group of 8); registers accumulate fp32 over the lane's pixels,
+// then fp64 shared/global atomics (one global atomic per channel per block).
+__global__ void __launch_bounds__(256) instnorm_stats_kernel(View x0, int x0_shift, View x1, int H, int W, int G, int PL,
+                                                            int chunk, const float* __restrict__ noise,
+                                                            const float* __restrict__ ns, double* __restrict__ acc) {
+  extern __shared__ double sh[];  // [G*8][2]
+  const int n = blockIdx.y;
+  const int C = G * 8;
+  for (int i = threadIdx.x; i < C * 2; i += blockDim.x) sh[i] = 0.0;
+  __syncthreads();
+  const int g = threadIdx.x % G;
+  const int pl = threadIdx.x / G;
+  if (pl < PL) {
+    const int c0 = g * 8;
+    const long long HW = (long long)H * W;
+    const long long p_begin = (long long)blockIdx.x * chunk;
+    long long p_end = p_begin + chunk;
+    if (p_end > HW) p_end = HW;
+    float s[8], q[8], nsv[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s[i] = 0.f; q[i] = 0.f; nsv[i] = ns ? __ldg(ns + c0 + i) : 0.f; }
+    const bool from0 = c0 < x0.c;
+    const int W0 = W >> x0_shift, H0 = H >> x0_shift;
+    for (long long p = p_begin + pl; p < p_end; p += PL) {
+      const int y = (int)(p / W), x = (int)(p - (long long)y * W);
+      const __nv_bfloat16* src =
+          from0 ? reinterpret_cast<const __nv_bfloat16*>(x0.ptr) + (((long long)n * H0 + (y >> x0_shift)) * W0 + (x >> x0_shift)) * x0.pitch + c0
+                : reinterpret_cast<const __nv_bfloat16*>(x1.ptr) + (((long long)n * H + y) * W + x) * x1.pitch + (c0 - x0.c);
+      float f[8];
+      unpack8(ldg16(src), f);
+      const float nz = noise ? __ldg(noise + (long long)n * HW + p) : 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float v = fmaf(nz, nsv[i], f[i]);
+        s[i] += v;
+        q[i] = fmaf(v, v, q[i]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      atomicAdd(&sh[(c0 + i) * 2], (double)s[i]);
+      atomicAdd(&sh[(c0 + i) * 2 + 1], (double)q[i]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C * 2; i += blockDim.x) atomicAdd(&acc[(long long)n * C * 2 + i], sh[i]);
+}
+
+__global__ void instnorm_finalize_kernel(const double* __restrict__ acc, int NC, double inv_hw, float eps,
+                                         float* __restrict__ mean, float* __restrict__ rstd) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= NC) return;
+  const double m = acc[2 * i] * inv_hw;
+  double var = acc[2 * i + 1] * inv_hw - m * m;
+  if (var < 0.0) var = 0.0;
+  mean[i] = (float)m;
+  rstd[i] = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+__global__ void instnorm_apply_kernel(View x, const float* __restrict__ mean, const float* __restrict__ rstd, int act, View y,
+                                      long long total, int G) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int g = (int)(idx % G);
+  const long long pix = idx / G;
+  const int n = (int)(pix / ((long long)x.h * x.w));
+  float f[8];
+  unpack8(ldg16(reinterpret_cast<const __nv_bfloat16*>(x.ptr) + pix * x.pitch + g * 8), f);
+  const float* mp = mean + (long long)n * x.c + g * 8;
+  const float* rp = rstd + (long long)n * x.c + g * 8;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const bool in = g * 8 + i < x.c;
+    f[i] = in ? apply_act((f[i] - __ldg(mp + i)) * __ldg(rp + i), act) : 0.f;
+  }
+  *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(y.ptr)) + pix * y.pitch + g * 8) = pack8(f);
+}
+
+// ------------------------------------------------------------------------------------------------ layout converters
+// thread = (dst pixel, 8-channel group); src fp32 NCHW with nearest resampling.
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, int C, int SH, int SW, View dst, int G, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int g = (int)(idx % G);
+  const long long pix = idx / G;
+  const int x = (int)(pix % dst.w);
+  const int y = (int)((pix / dst.w) % dst.h);
+  const int n = (int)(pix / ((long long)dst.w * dst.h));
+  // src = floor(dst * in / out): exact in integers
+  const int sy = (int)(((long long)y * SH) / dst.h);
+  const int sx = (int)(((long long)x * SW) / dst.w);
+  float f[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = g * 8 + i;
+    f[i] = c < C ? __ldg(src + (((long long)n * C + c) * SH + sy) * SW + sx) : 0.f;
+  }
+  *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(dst.ptr)) + pix * dst.pitch + g * 8) = pack8(f);
+}
+
+// thread = (pixel); loops channels; writes are coalesced per plane.
+__global__ void nhwc_to_nchw_kernel(View src, float* __restrict__ dst, long long npix) {
+  const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= npix) return;
+  const long long hw = (long long)src.h * src.w;
+  const int n = (int)(pix / hw);
+  const long long rem = pix - (long long)n * hw;
+  float* d = dst + (long long)n * src.c * hw + rem;
+  if (src.dtype == 0) {
+    const __nv_bfloat16* s = reinterpret_cast<const __nv_bfloat16*>(src.ptr) + pix * src.pitch;
+    for (int c = 0; c < src.c; ++c) d[(long long)c * hw] = __bfloat162float(s[c]);
+  } else {
+    const float* s = reinterpret_cast<const float*>(src.ptr) + pix * src.pitch;
+    for (int c = 0; c < src.c; ++c) d[(long long)c * hw] = s[c];
+  }
+}
+
+// thread = (dst pixel, sub-pixel 0..3, 8-channel group of src)
+__global__ void space_to_depth_kernel(View src, View dst, int G, int Gd, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int gd = (int)(idx % Gd);  // dst channel group
+  const long long pix = idx / Gd;
+  const int X = (int)(pix % dst.w);
+  const int Y = (int)((pix / dst.w) % dst.h);
+  const int n = (int)(pix / ((long long)dst.w * dst.h));
+  uint4 v = make_uint4(0, 0, 0, 0);
+  const int sub = gd / G, g = gd % G;
+  if (sub < 4) {
+    const int sy = 2 * Y + (sub >> 1), sx = 2 * X + (sub & 1);
+    if (sy < src.h && sx < src.w)
+      v = ldg16(reinterpret_cast<const __nv_bfloat16*>(src.ptr) + (((long long)n * src.h + sy) * src.w + sx) * src.pitch + g * 8);
+  }
+  *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(dst.ptr)) + pix * dst.pitch + gd * 8) = v;
+}
+
+__global__ void avgpool3s2_kernel(View src, View dst, int G, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int g = (int)(idx % G);
+  const long long pix = idx / G;
+  const int X = (int)(pix % dst.w);
+  const int Y = (int)((pix / dst.w) % dst.h);
+  const int n = (int)(pix / ((long long)dst.w * dst.h));
+  float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int cnt = 0;
+  for (int dy = -1; dy <= 1; ++dy) {
+    const int y = 2 * Y + dy;
+    if (y < 0 || y >= src.h) continue;
+    for (int dx = -1; dx <= 1; ++dx) {
+      const int x = 2 * X + dx;
+      if (x < 0 || x >= src.w) continue;
+      float f[8];
+      unpack8(ldg16(reinterpret_cast<const __nv_bfloat16*>(src.ptr) + (((long long)n * src.h + y) * src.w + x) * src.pitch + g * 8), f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s[i] += f[i];
+      ++cnt;
+    }
+  }
+  const float inv = 1.f / (float)cnt;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] *= inv;
+  *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(dst.ptr)) + pix * dst.pitch + g * 8) = pack8(s);
+}
+
+// F.interpolate(bilinear, x2, align_corners=False): s = max((d+0.5)/2-0.5, 0); i0=floor(s); i1=min(i0+1,n-1)
+__device__ __forceinline__ void up2_taps(int d, int n, int& i0, int& i1, float& w0, float& w1) {
+  float s = __fsub_rn(__fmul_rn(__fadd_rn((float)d, 0.5f), 0.5f), 0.5f);
+  s = fmaxf(s, 0.f);
+  const float fl = floorf(s);
+  i0 = (int)fl;
+  i1 = min(i0 + 1, n - 1);
+  w1 = __fsub_rn(s, fl);
+  w0 = __fsub_rn(1.f, w1);
+}
+
+__global__ void bilinear_up2_add_kernel(View a, View b, View dst, int G, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int g = (int)(idx % G);
+  const long long pix = idx / G;
+  const int x = (int)(pix % dst.w);
+  const int y = (int)((pix / dst.w) % dst.h);
+  const int n = (int)(pix / ((long long)dst.w * dst.h));
+  int x0, x1, y0, y1;
+  float wx0, wx1, wy0, wy1;
+  up2_taps(x, a.w, x0, x1, wx0, wx1);
+  up2_taps(y, a.h, y0, y1, wy0, wy1);
+  const __nv_bfloat16* ap = reinterpret_cast<const __nv_bfloat16*>(a.ptr) + (long long)n * a.h * a.w * a.pitch + g * 8;
+  float f00[8], f01[8], f10[8], f11[8], o[8];
+  unpack8(ldg16(ap + ((long long)y0 * a.w + x0) * a.pitch), f00);
+  unpack8(ldg16(ap + ((long long)y0 * a.w + x1) * a.pitch), f01);
+  unpack8(ldg16(ap + ((long long)y1 * a.w + x0) * a.pitch), f10);
+  unpack8(ldg16(ap + ((long long)y1 * a.w + x1) * a.pitch), f11);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[i] = wy0 * (wx0 * f00[i] + wx1 * f01[i]) + wy1 * (wx0 * f10[i] + wx1 * f11[i]);
+  if (b.ptr) {
+    float fb[8];
+    unpack8(ldg16(reinterpret_cast<const __nv_bfloat16*>(b.ptr) + pix * b.pitch + g * 8), fb);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] += fb[i];
+  }
+  *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(dst.ptr)) + pix * dst.pitch + g * 8) = pack8(o);
+}
+
+// ------------------------------------------------------------------------------------------------ flow warp
+// thread = (dst pixel, 8-channel group).  The coordinate chain uses explicitly rounded fp32 operations (no FMA
+// contraction) in the exact order of oracle/hrviton_oracle.py:np_flow_warp_coords so that the gather indices
+// are bit-exact.
+__global__ void flow_warp_kernel(const float* __restrict__ flow_lo, const float* __restrict__ lin_x, const float* __restrict__ lin_y,
+                                 View src, View dst, float* __restrict__ flow_up, int* __restrict__ idx_out, float sx, float sy,
+                                 int G, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int g = (int)(idx % G);
+  const long long pix = idx / G;
+  const int W = dst.w, H = dst.h;
+  const int x = (int)(pix % W);
+  const int y = (int)((pix / W) % H);
+  const int n = (int)(pix / ((long long)W * H));
+  const int hl = H >> 1, wl = W >> 1;
+  int xa, xb, ya, yb;
+  float wxa, wxb, wya, wyb;
+  up2_taps(x, wl, xa, xb, wxa, wxb);
+  up2_taps(y, hl, ya, yb, wya, wyb);
+  const float2* fl = reinterpret_cast<const float2*>(flow_lo) + (long long)n * hl * wl;
+  const float2 f00 = __ldg(fl + (long long)ya * wl + xa), f01 = __ldg(fl + (long long)ya * wl + xb);
+  const float2 f10 = __ldg(fl + (long long)yb * wl + xa), f11 = __ldg(fl + (long long)yb * wl + xb);
+  // lerp along x inside each source row, then along y (torch's CPU kernel order)
+  const float ux0 = __fadd_rn(__fmul_rn(f00.x, wxa), __fmul_rn(f01.x, wxb));
+  const float ux1 = __fadd_rn(__fmul_rn(f10.x, wxa), __fmul_rn(f11.x, wxb));
+  const float uy0 = __fadd_rn(__fmul_rn(f00.y, wxa), __fmul_rn(f01.y, wxb));
+  const float uy1 = __fadd_rn(__fmul_rn(f10.y, wxa), __fmul_rn(f11.y, wxb));
+  const float fx = __fadd_rn(__fmul_rn(ux0, wya), __fmul_rn(ux1, wyb));
+  const float fy = __fadd_rn(__fmul_rn(uy0, wya), __fmul_rn(uy1, wyb));
+  const float gx = __fadd_rn(__fdiv_rn(fx, sx), __ldg(lin_x + x));
+  const float gy = __fadd_rn(__fdiv_rn(fy, sy), __ldg(lin_y + y));
+  float ix = __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(gx, 1.f), (float)src.w), 1.f), 2.f);
+  float iy = __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(gy, 1.f), (float)src.h), 1.f), 2.f);
+  ix = fminf(fmaxf(ix, 0.f), (float)(src.w - 1));
+  iy = fminf(fmaxf(iy, 0.f), (float)(src.h - 1));
+  const float fx0 = floorf(ix), fy0 = floorf(iy);
+  const int x0 = (int)fx0, y0 = (int)fy0;
+  const float tx = __fsub_rn(ix, fx0), ty = __fsub_rn(iy, fy0);
+  if (g == 0) {
+    if (flow_up) reinterpret_cast<float2*>(flow_up)[pix] = make_float2(fx, fy);
+    if (idx_out) reinterpret_cast<int2*>(idx_out)[pix] = make_int2(x0, y0);
+  }
+  if (g * 8 >= ((src.c + 7) & ~7)) return;
+  const int x1 = min(x0 + 1, src.w - 1), y1 = min(y0 + 1, src.h - 1);
+  const float wx1 = (x0 + 1 <= src.w - 1) ? tx : 0.f, wy1 = (y0 + 1 <= src.h - 1) ? ty : 0.f;
+  const float wx0 = 1.f - tx, wy0 = 1.f - ty;
+  const float w00 = wy0 * wx0, w01 = wy0 * wx1, w10 = wy1 * wx0, w11 = wy1 * wx1;
+  float o[8];
+  const long long ib = (long long)n * src.h * src.w;
+  if (src.dtype == 0) {
+    const __nv_bfloat16* sp = reinterpret_cast<const __nv_bfloat16*>(src.ptr) + g * 8;
+    float a[8], b[8], c[8], d[8];
+    unpack8(ldg16(sp + (ib + (long long)y0 * src.w + x0) * src.pitch), a);
+    unpack8(ldg16(sp + (ib + (long long)y0 * src.w + x1) * src.pitch), b);
+    unpack8(ldg16(sp + (ib + (long long)y1 * src.w + x0) * src.pitch), c);
+    unpack8(ldg16(sp + (ib + (long long)y1 * src.w + x1) * src.pitch), d);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = a[i] * w00 + b[i] * w01 + c[i] * w10 + d[i] * w11;
+  } else {
+    const float* sp = reinterpret_cast<const float*>(src.ptr) + g * 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (g * 8 + i < src.c) {
+        o[i] = __ldg(sp + (ib + (long long)y0 * src.w + x0) * src.pitch + i) * w00 + __ldg(sp + (ib + (long long)y0 * src.w + x1) * src.pitch + i) * w01 +
+               __ldg(sp + (ib + (long long)y1 * src.w + x0) * src.pitch + i) * w10 + __ldg(sp + (ib + (long long)y1 * src.w + x1) * src.pitch + i) * w11;
+      } else {
+        o[i] = 0.f;
+      }
+    }
+  }
+  if (dst.dtype == 0) {
+    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(dst.ptr)) + pix * dst.pitch + g * 8) = pack8(o);
+  } else {
+    float* dp = reinterpret_cast<float*>(const_cast<void*>(dst.ptr)) + pix * dst.pitch + g * 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (g * 8 + i < dst.c) dp[i] = o[i];
+  }
+}
+
+static int check_bf16_vec(const hrv_tensor* t, const char* what) {
+  if (!t || !t->ptr) return set_error(HRV_EINVAL, "%s: null tensor", what);
+  if (t->dtype != HRV_BF16) return set_error(HRV_EINVAL, "%s: must be bf16", what);
+  if (((uintptr_t)t->ptr & 15) || (t->pitch % 8)) return set_error(HRV_EINVAL, "%s: needs 16-byte alignment and pitch %% 8 == 0", what);
+  return 0;
+}
+static int launch_ok(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(HRV_ECUDA, "%s launch: %s", what, cudaGetErrorString(e));
+  return HRV_OK;
+}
+static inline unsigned blocks_for(long long total, int bs) { return (unsigned)((total + bs - 1) / bs); }
+
+}  // namespace hrv
+
+using namespace hrv;
+
+extern "C" int hrv_instnorm_stats(const hrv_tensor* x0, int32_t x0_shift, const hrv_tensor* x1, int32_t h, int32_t w,
+                                  const float* noise, const float* noise_scale, float eps, float* mean, float* rstd,
+                                  void* workspace, size_t workspace_bytes, hrv_stream stream) {
+  int rc = check_bf16_vec(x0, "instnorm_stats x0");
+  if (rc) return rc;
+  const bool has1 = x1 && x1->ptr;
+  if (has1 && (rc = check_bf16_vec(x1, "instnorm_stats x1"))) return rc;
+  const int C = x0->c + (has1 ? x1->c : 0);
+  if ((x0->c % 8) || (C % 8)) return set_error(HRV_EINVAL, "instnorm_stats: channel counts must be multiples of 8");
+  if (C / 8 > 256) return set_error(HRV_EUNSUPPORTED, "instnorm_stats: more than 2048 channels");
+  if ((x0->h << x0_shift) != h || (x0->w << x0_shift) != w) return set_error(HRV_EINVAL, "instnorm_stats: x0 extent mismatch");
+  if (has1 && (x1->h != h || x1->w != w || x1->n != x0->n)) return set_error(HRV_EINVAL, "instnorm_stats: x1 extent mismatch");
+  const int N = x0->n;
+  const size_t need = (size_t)N * C * 2 * sizeof(double);
+  if (!workspace || workspace_bytes < need) return set_error(HRV_EINVAL, "instnorm_stats: workspace too small (%zu < %zu)", workspace_bytes, need);
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(workspace, 0, need, st);
+  const int G = C / 8;
+  const int PL = 256 / G;
+  const long long HW = (long long)h * w;
+  long long target_blocks = (long long)sm_count() * 8 / (N > 0 ? N : 1);
+  if (target_blocks < 1) target_blocks = 1;
+  long long chunk = (HW + target_blocks - 1) / target_blocks;
+  const long long min_chunk = (long long)PL * 16;
+  if (chunk < min_chunk) chunk = min_chunk;
+  const unsigned gx = (unsigned)((HW + chunk - 1) / chunk);
+  instnorm_stats_kernel<<<dim3(gx, N), 256, (size_t)C * 2 * sizeof(double), st>>>(mk(x0), x0_shift, mk(has1 ? x1 : nullptr), h, w, G, PL,
+                                                                                 (int)chunk, noise, noise_scale, (double*)workspace);
+  if ((rc = launch_ok("instnorm_stats"))) return rc;
+  instnorm_finalize_kernel<<<blocks_for(N * C, 256), 256, 0, st>>>((const double*)workspace, N * C, 1.0 / (double)HW, eps, mean, rstd);
+  return launch_ok("instnorm_finalize");
+}
+
+extern "C" int hrv_instnorm_apply(const hrv_tensor* x, const float* mean, const float* rstd, int32_t act, const hrv_tensor* y,
+                                  hrv_stream stream) {
+  int rc;
+  if ((rc = check_bf16_vec(x, "instnorm_apply x")) || (rc = check_bf16_vec(y, "instnorm_apply y"))) return rc;
+  const int G = (x->c + 7) / 8;
+  const long long total = (long long)x->n * x->h * x->w * G;
+  instnorm_apply_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(mk(x), mean, rstd, act, mk(y), total, G);
+  return launch_ok("instnorm_apply");
+}
+
+extern "C" int hrv_nchw_to_nhwc(const float* src, int32_t c, int32_t src_h, int32_t src_w, const hrv_tensor* dst, hrv_stream stream) {
+  int rc = check_bf16_vec(dst, "nchw_to_nhwc dst");
+  if (rc) return rc;
+  const int G = (dst->c + 7) / 8;
+  if (G * 8 > dst->pitch) return set_error(HRV_EINVAL, "nchw_to_nhwc: dst pitch too small for padded channels");
+  const long long total = (long long)dst->n * dst->h * dst->w * G;
+  nchw_to_nhwc_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(src, c, src_h, src_w, mk(dst), G, total);
+  return launch_ok("nchw_to_nhwc");
+}
+
+extern "C" int hrv_nhwc_to_nchw(const hrv_tensor* src, float* dst, hrv_stream stream) {
+  if (!src || !src->ptr || !dst) return set_error(HRV_EINVAL, "nhwc_to_nchw: null");
+  const long long npix = (long long)src->n * src->h * src->w;
+  nhwc_to_nchw_kernel<<<blocks_for(npix, 256), 256, 0, (cudaStream_t)stream>>>(mk(src), dst, npix);
+  return launch_ok("nhwc_to_nchw");
+}
+
+extern "C" int hrv_space_to_depth(const hrv_tensor* src, const hrv_tensor* dst, hrv_stream stream) {
+  int rc;
+  if ((rc = check_bf16_vec(src, "s2d src")) || (rc = check_bf16_vec(dst, "s2d dst"))) return rc;
+  const int G = (src->c + 7) / 8;
+  if (dst->h != (src->h + 1) / 2 || dst->w != (src->w + 1) / 2 || dst->c < 4 * G * 8 || (dst->c % 8))
+    return set_error(HRV_EINVAL, "s2d: dst must be ceil(h/2) x ceil(w/2) x (>= 4*roundup8(c))");
+  const int Gd = dst->c / 8;
+  const long long total = (long long)dst->n * dst->h * dst->w * Gd;
+  space_to_depth_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(mk(src), mk(dst), G, Gd, total);
+  return launch_ok("space_to_depth");
+}
+
+extern "C" int hrv_avgpool3s2(const hrv_tensor* src, const hrv_tensor* dst, hrv_stream stream) {
+  int rc;
+  if ((rc = check_bf16_vec(src, "avgpool src")) || (rc = check_bf16_vec(dst, "avgpool dst"))) return rc;
+  if (dst->h != (src->h - 1) / 2 + 1 || dst->w != (src->w - 1) / 2 + 1) return set_error(HRV_EINVAL, "avgpool: dst extent");
+  const int G = (src->c + 7) / 8;
+  const long long total = (long long)dst->n * dst->h * dst->w * G;
+  avgpool3s2_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(mk(src), mk(dst), G, total);
+  return launch_ok("avgpool3s2");
+}
+
+extern "C" int hrv_bilinear_up2_add(const hrv_tensor* a, const hrv_tensor* b, const hrv_tensor* dst, hrv_stream stream) {
+  int rc;
+  if ((rc = check_bf16_vec(a, "up2 a")) || (rc = check_bf16_vec(dst, "up2 dst"))) return rc;
+  const bool hb = b && b->ptr;
+  if (hb && (rc = check_bf16_vec(b, "up2 b"))) return rc;
+  if (dst->h != 2 * a->h || dst->w != 2 * a->w) return set_error(HRV_EINVAL, "up2: dst must be 2x");
+  const int G = (a->c + 7) / 8;
+  const long long total = (long long)dst->n * dst->h * dst->w * G;
+  bilinear_up2_add_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(mk(a), mk(hb ? b : nullptr), mk(dst), G, total);
+  return launch_ok("bilinear_up2_add");
+}
+
+extern "C" int hrv_flow_warp(const float* flow_lo, const float* lin_x, const float* lin_y, const hrv_tensor* src, const hrv_tensor* dst,
+                             float* flow_up, int32_t* idx_out, hrv_stream stream) {
+  if (!flow_lo || !lin_x || !lin_y || !src || !dst || !src->ptr || !dst->ptr) return set_error(HRV_EINVAL, "flow_warp: null argument");
+  if ((dst->h & 1) || (dst->w & 1)) return set_error(HRV_EINVAL, "flow_warp: output extent must be even");
+  if (src->dtype == HRV_BF16 && (((uintptr_t)src->ptr & 15) || (src->pitch % 8))) return set_error(HRV_EINVAL, "flow_warp: src alignment");
+  if (dst->dtype == HRV_BF16 && (((uintptr_t)dst->ptr & 15) || (dst->pitch % 8))) return set_error(HRV_EINVAL, "flow_warp: dst alignment");
+  if (src->n != dst->n || src->c != dst->c) return set_error(HRV_EINVAL, "flow_warp: src/dst mismatch");
+  const int G = (src->c + 7) / 8;
+  const long long total = (long long)dst->n * dst->h * dst->w * G;
+  // Python-float arithmetic of the reference ((iW/2 - 1.0)/2.0), rounded once to fp32 as torch does for a scalar divisor
+  const float sx = (float)((dst->w / 2.0 - 1.0) / 2.0);
+  const float sy = (float)((dst->h / 2.0 - 1.0) / 2.0);
+  flow_warp_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(flow_lo, lin_x, lin_y, mk(src), mk(dst), flow_up, idx_out, sx, sy, G, total);
+  return launch_ok("flow_warp");
+}

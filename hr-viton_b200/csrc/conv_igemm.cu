@@ -1,0 +1,426 @@
+// conv_igemm.cu — NHWC convolution as an im2col-free implicit GEMM on sm_100a.
+//
+//   GEMM view:  M = output pixels (128 per tile = TN x TH x TW box), N = output channels (BN <= 256 per tile),
+//               K = taps x input channels, walked tap by tap in chunks of BK channels.
+//   A operand:  one TMA 4-D box {BK ch, TW, TH, TN} of the NHWC input per (tap, channel chunk), shifted by the tap
+//               offset; TMA zero-fills out-of-range pixels (= the convolution's zero padding) and channels.
+//   B operand:  one TMA 2-D box {BK, BN} of the packed weights [n_pad][taps*cin_k] (K-major).
+//   MMA:        tcgen05.mma.cta_group::1.kind::f16, M=128 x N=BN x K=16, bf16 inputs, fp32 accumulators in TMEM.
+//   Pipeline:   persistent CTAs (one per SM); warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
+//               warps 4-7 = epilogue.  smem ring of `stages` (A,B) buffers with full/empty mbarriers; TMEM holds two
+//               accumulator buffers so the epilogue of tile i overlaps the MMAs of tile i+1.
+//   Epilogues:  LINEAR  out = act(acc*scale + shift (+ residual))      (bias / folded BatchNorm / residual / tanh)
+//               SPADE   out = act((x + noise*ns - mean)*rstd*(1+gamma) + beta), gamma/beta = interleaved GEMM columns:
+//                       the SPADE modulation never leaves registers (network_generator.py:115-121,170-171).
+//
+// Replaces nn.Conv2d at networks.py:60-93,178-192 and network_generator.py:97-99,132-135,184-201,263-272.
+#include "hrv_host.h"
+#include "hrv_ptx.cuh"
+
+namespace hrv {
+
+constexpr int kMaxStages = 8;
+constexpr int kThreads = 256;
+
+struct alignas(64) ConvArgs {
+  CUtensorMap tmA;
+  CUtensorMap tmB;
+  int Nimg, Hout, Wout;
+  int tw_log, th_log;
+  int tiles_x, tiles_y, tiles_img, tiles_n;
+  int KH, KW, off_y, off_x, chunks;
+  int BN, stages, n_gemm;
+  int epi, act;
+  const float* scale;
+  const float* shift;
+  void* out;
+  int out_pitch, out_dtype, out_layout, out_c;
+  const void* res;
+  int res_pitch, res_dtype;
+  const __nv_bfloat16* x0;
+  int x0_c, x0_pitch, x0_shift;
+  const __nv_bfloat16* x1;
+  int x1_pitch;
+  const float* mean;
+  const float* rstd;
+  const float* noise;
+  const float* noise_scale;
+  int C_mod;
+};
+
+template <int BK>
+__global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvArgs a) {
+  constexpr uint32_t ROW_BYTES = BK * 2;               // one K chunk of one pixel / one output channel
+  constexpr uint32_t A_BYTES = 128 * ROW_BYTES;        // 128 pixels
+  constexpr uint32_t SBO = 8 * ROW_BYTES;              // 8-row core-matrix group stride
+  constexpr uint32_t LAYOUT = (BK == 64) ? 2u : (BK == 32 ? 4u : 6u);  // SW128 / SW64 / SW32
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  // control block: [0,1024): barriers + tmem pointer ; stages follow, each 1024-aligned
+  auto bar_full = [&](int s) { return base + 8u * s; };
+  auto bar_empty = [&](int s) { return base + 8u * (kMaxStages + s); };
+  auto bar_tfull = [&](int i) { return base + 8u * (2 * kMaxStages + i); };
+  auto bar_tempty = [&](int i) { return base + 8u * (2 * kMaxStages + 2 + i); };
+  const uint32_t tmem_slot = base + 8u * (2 * kMaxStages + 4);
+  const uint32_t b_bytes = (uint32_t)a.BN * ROW_BYTES;
+  const uint32_t stage_bytes = A_BYTES + ((b_bytes + 1023u) & ~1023u);
+  const uint32_t stage0 = base + 1024u;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int S = a.stages;
+  const int KT = a.KH * a.KW * a.chunks;
+  const int total_tiles = a.tiles_n * a.tiles_x * a.tiles_y * a.tiles_img;
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < 2u * a.BN) tmem_cols <<= 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&a.tmA);
+    tma_prefetch_desc(&a.tmB);
+  } else if (warp == 1 && lane == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(bar_full(s), 1);
+      mbar_init(bar_empty(s), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_tfull(i), 1);
+      mbar_init(bar_tempty(i), 128);
+    }
+    fence_mbar_init();
+  } else if (warp == 2) {
+    tmem_alloc(tmem_slot, tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+
+  if (warp == 0 && lane == 0) {
+    // ===================================================== TMA producer
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int nt = tile % a.tiles_n;
+      int mt = tile / a.tiles_n;
+      const int tx = mt % a.tiles_x;
+      mt /= a.tiles_x;
+      const int ty = mt % a.tiles_y;
+      const int ti = mt / a.tiles_y;
+      const int x0 = (tx << a.tw_log) - a.off_x;
+      const int y0 = (ty << a.th_log) - a.off_y;
+      const int n0 = ti << (7 - a.tw_log - a.th_log);
+      int kcol = 0;
+      for (int ky = 0; ky < a.KH; ++ky) {
+        for (int kx = 0; kx < a.KW; ++kx) {
+          for (int kc = 0; kc < a.chunks; ++kc, ++it, kcol += BK) {
+            const int s = it % S;
+            const uint32_t ph = (it / S) & 1u;
+            mbar_wait(bar_empty(s), ph ^ 1u);
+            mbar_arrive_expect_tx(bar_full(s), A_BYTES + b_bytes);
+            const uint32_t sa = stage0 + s * stage_bytes;
+            tma_load_4d(sa, &a.tmA, bar_full(s), kc * BK, x0 + kx, y0 + ky, n0);
+            tma_load_2d(sa + A_BYTES, &a.tmB, bar_full(s), kcol, nt * a.BN);
+          }
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================================================== MMA issuer (single thread)
+    const uint32_t idesc = make_idesc_bf16(128, (uint32_t)a.BN);
+    uint32_t it = 0, tcount = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+      const uint32_t acc = tcount & 1u;
+      const uint32_t aph = (tcount >> 1) & 1u;
+      mbar_wait(bar_tempty(acc), aph ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * (uint32_t)a.BN;
+      for (int k = 0; k < KT; ++k, ++it) {
+        const int s = it % S;
+        const uint32_t ph = (it / S) & 1u;
+        mbar_wait(bar_full(s), ph);
+        tc_fence_after();
+        const uint32_t sa = stage0 + s * stage_bytes;
+        const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < BK / 16; ++kk) {
+          const uint64_t da = make_smem_desc(sa + kk * 32, SBO, LAYOUT);
+          const uint64_t db = make_smem_desc(sb + kk * 32, SBO, LAYOUT);
+          umma_f16(d_tmem, da, db, idesc, (uint32_t)((k | kk) != 0));
+        }
+        umma_commit(bar_empty(s));  // frees this smem stage once the MMAs above have read it
+      }
+      umma_commit(bar_tfull(acc));  // accumulator complete -> epilogue
+    }
+  } else if (warp >= 4) {
+    // ===================================================== epilogue (4 warps, one TMEM lane = one pixel per thread)
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int tw_mask = (1 << a.tw_log) - 1, th_mask = (1 << a.th_log) - 1;
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+      const int nt = tile % a.tiles_n;
+      int mt = tile / a.tiles_n;
+      const int tx = mt % a.tiles_x;
+      mt /= a.tiles_x;
+      const int ty = mt % a.tiles_y;
+      const int ti = mt / a.tiles_y;
+      const int x = (tx << a.tw_log) + (r & tw_mask);
+      const int y = (ty << a.th_log) + ((r >> a.tw_log) & th_mask);
+      const int n = (ti << (7 - a.tw_log - a.th_log)) + (r >> (a.tw_log + a.th_log));
+      const bool valid = (x < a.Wout) && (y < a.Hout) && (n < a.Nimg);
+      const long long pix = ((long long)n * a.Hout + y) * a.Wout + x;
+
+      const uint32_t acc = tcount & 1u;
+      const uint32_t aph = (tcount >> 1) & 1u;
+      mbar_wait(bar_tfull(acc), aph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)a.BN;
+      const int n_base = nt * a.BN;
+
+      if (a.epi == 0) {
+        // ---------------- LINEAR
+        const int store_c = (a.out_dtype == 0 && a.out_layout == 0) ? ((a.out_c + 7) & ~7) : a.out_c;
+        for (int col = 0; col < a.BN; col += 16) {
+          uint32_t v[16];
+          __syncwarp();
+          tmem_ld16(taddr + col, v);
+          tmem_wait_ld();
+          const int j0 = n_base + col;
+          if (!valid || j0 >= store_c) continue;
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            const int jg = j0 + g * 8;
+            if (jg >= store_c) break;
+            float f[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int j = jg + i;
+              const bool in = j < a.n_gemm;
+              const float sc = in ? (a.scale ? __ldg(a.scale + j) : 1.f) : 0.f;
+              const float sh = (in && a.shift) ? __ldg(a.shift + j) : 0.f;
+              f[i] = fmaf(__uint_as_float(v[g * 8 + i]), sc, sh);
+            }
+            if (a.res) {
+              if (a.res_dtype == 0) {
+                const uint4 rv = __ldg(reinterpret_cast<const uint4*>(
+                    reinterpret_cast<const __nv_bfloat16*>(a.res) + pix * a.res_pitch + jg));
+                f[0] += bf16_lo(rv.x); f[1] += bf16_hi(rv.x); f[2] += bf16_lo(rv.y); f[3] += bf16_hi(rv.y);
+                f[4] += bf16_lo(rv.z); f[5] += bf16_hi(rv.z); f[6] += bf16_lo(rv.w); f[7] += bf16_hi(rv.w);
+              } else {
+                const float* rp = reinterpret_cast<const float*>(a.res) + pix * a.res_pitch + jg;
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                  if (jg + i < a.out_c) f[i] += __ldg(rp + i);
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = apply_act(f[i], a.act);
+            if (a.out_dtype == 0) {
+              uint4 o;
+              o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]);
+              o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
+              *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) + pix * a.out_pitch + jg) = o;
+            } else if (a.out_layout == 0) {
+              float* op = reinterpret_cast<float*>(a.out) + pix * a.out_pitch + jg;
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                if (jg + i < a.out_c) op[i] = f[i];
+            } else {  // fp32 NCHW
+              float* op = reinterpret_cast<float*>(a.out);
+              const long long hw = (long long)a.Hout * a.Wout;
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                if (jg + i < a.out_c) op[((long long)n * a.out_c + jg + i) * hw + (long long)y * a.Wout + x] = f[i];
+            }
+          }
+        }
+      } else {
+        // ---------------- SPADE: 16 GEMM columns = 8 channels of (gamma, beta)
+        const int sh0 = a.x0_shift;
+        const long long pix0 = ((long long)n * (a.Hout >> sh0) + (y >> sh0)) * (a.Wout >> sh0) + (x >> sh0);
+        const float nz = (valid && a.noise) ? __ldg(a.noise + pix) : 0.f;
+        for (int col = 0; col < a.BN; col += 16) {
+          uint32_t v[16];
+          __syncwarp();
+          tmem_ld16(taddr + col, v);
+          tmem_wait_ld();
+          const int c0 = (n_base + col) >> 1;
+          if (!valid || c0 >= a.C_mod) continue;
+          const __nv_bfloat16* xp = (c0 < a.x0_c) ? (a.x0 + pix0 * a.x0_pitch + c0)
+                                                   : (a.x1 + pix * a.x1_pitch + (c0 - a.x0_c));
+          const uint4 xv = __ldg(reinterpret_cast<const uint4*>(xp));
+          float xs[8] = {bf16_lo(xv.x), bf16_hi(xv.x), bf16_lo(xv.y), bf16_hi(xv.y),
+                         bf16_lo(xv.z), bf16_hi(xv.z), bf16_lo(xv.w), bf16_hi(xv.w)};
+          float o[8];
+          const float* mp = a.mean + (long long)n * a.C_mod + c0;
+          const float* rp = a.rstd + (long long)n * a.C_mod + c0;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int c = c0 + i;
+            float xval = xs[i];
+            if (a.noise_scale) xval = fmaf(nz, __ldg(a.noise_scale + c), xval);
+            float gm = __uint_as_float(v[2 * i]);
+            float bt = __uint_as_float(v[2 * i + 1]);
+            if (a.shift) {
+              gm += __ldg(a.shift + 2 * c);
+              bt += __ldg(a.shift + 2 * c + 1);
+            }
+            const float xn = (xval - __ldg(mp + i)) * __ldg(rp + i);
+            o[i] = apply_act(fmaf(xn, 1.f + gm, bt), a.act);
+          }
+          uint4 ov;
+          ov.x = pack_bf16(o[0], o[1]); ov.y = pack_bf16(o[2], o[3]);
+          ov.z = pack_bf16(o[4], o[5]); ov.w = pack_bf16(o[6], o[7]);
+          *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) + pix * a.out_pitch + c0) = ov;
+        }
+      }
+      __syncwarp();
+      tc_fence_before();
+      mbar_arrive(bar_tempty(acc));
+    }
+  }
+
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+
+static int log2i(int v) {
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return l;
+}
+
+// Pick the power-of-two tile extent p <= cap for a dimension of size `dim`: least padding, ties -> larger.
+static int pick_pow2(int dim, int cap) {
+  int best = 1;
+  double best_waste = 1e30;
+  for (int p = 1; p <= cap; p <<= 1) {
+    const int tiles = (dim + p - 1) / p;
+    const double waste = (double)tiles * p / dim;
+    if (waste <= best_waste + 0.031) {
+      if (waste < best_waste) best_waste = waste;
+      best = p;
+    }
+  }
+  return best;
+}
+
+template <int BK>
+static int launch_conv(const ConvArgs& args, int grid, size_t smem, cudaStream_t st) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (e != cudaSuccess) return set_error(HRV_ECUDA, "cudaFuncSetAttribute(conv_igemm): %s", cudaGetErrorString(e));
+    attr_done = true;
+  }
+  conv_igemm_kernel<BK><<<grid, kThreads, smem, st>>>(args);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(HRV_ECUDA, "conv_igemm launch: %s", cudaGetErrorString(e));
+  return HRV_OK;
+}
+
+}  // namespace hrv
+
+using namespace hrv;
+
+extern "C" int hrv_conv2d_fwd(const hrv_conv_params* p, hrv_stream stream) {
+  if (!p) return set_error(HRV_EINVAL, "conv: null params");
+  const hrv_tensor& in = p->in;
+  const hrv_tensor& out = p->out;
+  if (in.dtype != HRV_BF16) return set_error(HRV_EINVAL, "conv: input must be bf16 NHWC");
+  if (((uintptr_t)in.ptr & 15) || (in.pitch % 8) || in.pitch < in.c)
+    return set_error(HRV_EINVAL, "conv: input needs 16-byte aligned ptr and pitch %% 8 == 0 (pitch=%d c=%d)", in.pitch, in.c);
+  if (p->bk != 64 && p->bk != 32 && p->bk != 16) return set_error(HRV_EINVAL, "conv: bk must be 64/32/16");
+  if (p->bn < 16 || p->bn > 256 || (p->bn % 16)) return set_error(HRV_EINVAL, "conv: bn=%d must be a multiple of 16 in [16,256]", p->bn);
+  if (p->kh < 1 || p->kw < 1 || p->n_gemm < 1) return set_error(HRV_EINVAL, "conv: bad kh/kw/n_gemm");
+  if (out.n != in.n) return set_error(HRV_EINVAL, "conv: batch mismatch");
+  if (((uintptr_t)p->wpack & 15)) return set_error(HRV_EINVAL, "conv: wpack must be 16-byte aligned");
+  if (out.dtype == HRV_BF16 && (p->out_layout != HRV_NHWC || ((uintptr_t)out.ptr & 15) || (out.pitch % 8)))
+    return set_error(HRV_EINVAL, "conv: bf16 output must be NHWC, 16-byte aligned, pitch %% 8 == 0");
+  if (p->res.ptr && p->res.dtype == HRV_BF16 && (((uintptr_t)p->res.ptr & 15) || (p->res.pitch % 8)))
+    return set_error(HRV_EINVAL, "conv: bf16 residual must be 16-byte aligned with pitch %% 8 == 0");
+
+  ConvArgs a;
+  memset(&a, 0, sizeof(a));
+  a.Nimg = out.n; a.Hout = out.h; a.Wout = out.w;
+  const int TW = pick_pow2(out.w, 128);
+  const int TH = pick_pow2(out.h, 128 / TW);
+  const int TN = 128 / (TW * TH);
+  a.tw_log = log2i(TW); a.th_log = log2i(TH);
+  a.tiles_x = (out.w + TW - 1) / TW;
+  a.tiles_y = (out.h + TH - 1) / TH;
+  a.tiles_img = (out.n + TN - 1) / TN;
+  a.tiles_n = (p->n_gemm + p->bn - 1) / p->bn;
+  a.KH = p->kh; a.KW = p->kw; a.off_y = p->off_y; a.off_x = p->off_x;
+  a.chunks = (in.c + p->bk - 1) / p->bk;
+  a.BN = p->bn; a.n_gemm = p->n_gemm;
+  a.epi = p->epi; a.act = p->act;
+  a.scale = p->scale; a.shift = p->shift;
+  a.out = out.ptr; a.out_pitch = out.pitch; a.out_dtype = out.dtype; a.out_layout = p->out_layout; a.out_c = out.c;
+  a.res = p->res.ptr; a.res_pitch = p->res.pitch; a.res_dtype = p->res.dtype;
+
+  if (p->epi == HRV_EPI_SPADE) {
+    const int C = p->x0.c + (p->x1.ptr ? p->x1.c : 0);
+    if (p->n_gemm != 2 * C) return set_error(HRV_EINVAL, "conv(spade): n_gemm=%d must equal 2*(x0.c+x1.c)=%d", p->n_gemm, 2 * C);
+    if ((p->x0.c % 8) || (C % 8) || out.dtype != HRV_BF16 || !p->mean || !p->rstd || !p->x0.ptr)
+      return set_error(HRV_EINVAL, "conv(spade): channel counts must be multiples of 8, output bf16, mean/rstd/x0 set");
+    if (((uintptr_t)p->x0.ptr & 15) || (p->x0.pitch % 8) || (p->x1.ptr && (((uintptr_t)p->x1.ptr & 15) || (p->x1.pitch % 8))))
+      return set_error(HRV_EINVAL, "conv(spade): x0/x1 alignment");
+    if (p->x0_shift && ((out.h & 1) || (out.w & 1) || p->x0.h * 2 != out.h || p->x0.w * 2 != out.w))
+      return set_error(HRV_EINVAL, "conv(spade): x0_shift needs x0 at exactly half resolution");
+    if (!p->x0_shift && (p->x0.h != out.h || p->x0.w != out.w)) return set_error(HRV_EINVAL, "conv(spade): x0 extent mismatch");
+    if (out.c != C) return set_error(HRV_EINVAL, "conv(spade): out.c must equal C");
+    a.x0 = (const __nv_bfloat16*)p->x0.ptr; a.x0_c = p->x0.c; a.x0_pitch = p->x0.pitch; a.x0_shift = p->x0_shift ? 1 : 0;
+    a.x1 = (const __nv_bfloat16*)p->x1.ptr; a.x1_pitch = p->x1.pitch;
+    a.mean = p->mean; a.rstd = p->rstd; a.noise = p->noise; a.noise_scale = p->noise_scale; a.C_mod = C;
+  } else if (p->epi != HRV_EPI_LINEAR) {
+    return set_error(HRV_EINVAL, "conv: unknown epilogue %d", p->epi);
+  }
+
+  // ---- tensor maps
+  const int elem = 2;
+  const CUtensorMapSwizzle sw = p->bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (p->bk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)in.c, (cuuint64_t)in.w, (cuuint64_t)in.h, (cuuint64_t)in.n};
+    cuuint64_t strides[3] = {(cuuint64_t)in.pitch * elem, (cuuint64_t)in.w * in.pitch * elem, (cuuint64_t)in.h * in.w * in.pitch * elem};
+    cuuint32_t box[4] = {(cuuint32_t)p->bk, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TN};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    int rc = encode_tensor_map(&a.tmA, 4, in.ptr, dims, strides, box, es, sw);
+    if (rc) return rc;
+  }
+  {
+    const cuuint64_t ktot = (cuuint64_t)p->kh * p->kw * a.chunks * p->bk;
+    cuuint64_t dims[2] = {ktot, (cuuint64_t)a.tiles_n * p->bn};
+    cuuint64_t strides[1] = {ktot * elem};
+    cuuint32_t box[2] = {(cuuint32_t)p->bk, (cuuint32_t)p->bn};
+    cuuint32_t es[2] = {1, 1};
+    int rc = encode_tensor_map(&a.tmB, 2, const_cast<void*>(p->wpack), dims, strides, box, es, sw);
+    if (rc) return rc;
+  }
+
+  const uint32_t row_bytes = p->bk * 2;
+  const uint32_t stage_bytes = 128 * row_bytes + (((uint32_t)p->bn * row_bytes + 1023u) & ~1023u);
+  int stages = (int)((225u * 1024u - 2048u) / stage_bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) return set_error(HRV_EINVAL, "conv: tile too large for shared memory");
+  a.stages = stages;
+  size_t smem = 2048 + (size_t)stages * stage_bytes;
+  if (smem < 120 * 1024) smem = 120 * 1024;  // force one CTA per SM (TMEM: up to 512 columns per CTA)
+
+  const long long total = (long long)a.tiles_n * a.tiles_x * a.tiles_y * a.tiles_img;
+  int grid = sm_count();
+  if (total < grid) grid = (int)total;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (p->bk) {
+    case 64: return launch_conv<64>(a, grid, smem, st);
+    case 32: return launch_conv<32>(a, grid, smem, st);
+    default: return launch_conv<16>(a, grid, smem, st);
+  }
+}

@@ -1,0 +1,286 @@
+"""NHWC activation views + thin wrappers over the C-ABI.  torch is used here for device memory and streams only."""
+import ctypes
+from dataclasses import dataclass
+
+import torch
+
+from . import capi
+from .capi import ACT_LRELU, ACT_NONE, ACT_RELU, ACT_TANH, BF16, F32  # noqa: F401
+
+LAUNCHES = [0]  # count of C-ABI kernel-launching calls (bench.py reads this for `gpu_launches`)
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def round_up(v, m):
+    return (v + m - 1) // m * m
+
+
+class Act:
+    """A pixel-major (NHWC) activation: `buf` is (N,H,W,P) bf16|fp32 on the GPU; the view covers channels
+    [c0, c0+c) of every pixel.  Channel slices of one buffer replace torch.cat."""
+
+    def __init__(self, buf, c=None, c0=0):
+        assert buf.is_cuda and buf.dim() == 4 and buf.is_contiguous(), "Act needs a contiguous CUDA (N,H,W,P) buffer"
+        self.buf = buf
+        self.c0 = c0
+        self.c = buf.shape[3] - c0 if c is None else c
+        assert self.c0 + self.c <= buf.shape[3]
+
+    @staticmethod
+    def empty(n, h, w, c, dtype=torch.bfloat16, device="cuda", pitch=None, zero=False):
+        p = round_up(c, 8) if pitch is None else pitch
+        f = torch.zeros if zero else torch.empty
+        return Act(f((n, h, w, p), dtype=dtype, device=device), c=c)
+
+    n = property(lambda s: s.buf.shape[0])
+    h = property(lambda s: s.buf.shape[1])
+    w = property(lambda s: s.buf.shape[2])
+    pitch = property(lambda s: s.buf.shape[3])
+
+    def slice(self, c0, c):
+        return Act(self.buf, c=c, c0=self.c0 + c0)
+
+    def ct(self):
+        es = self.buf.element_size()
+        return capi.Tensor(self.buf.data_ptr() + self.c0 * es, self.n, self.h, self.w, self.c, self.pitch,
+                           BF16 if self.buf.dtype == torch.bfloat16 else F32)
+
+    def to_nchw(self):
+        """fp32 NCHW copy (API boundary / tests)."""
+        out = torch.empty((self.n, self.c, self.h, self.w), dtype=torch.float32, device=self.buf.device)
+        t = self.ct()
+        capi.check(capi.lib().hrv_nhwc_to_nchw(ctypes.byref(t), out.data_ptr(), _stream()), "nhwc_to_nchw")
+        LAUNCHES[0] += 1
+        return out
+
+
+_NULL = capi.Tensor(None, 0, 0, 0, 0, 0, 0)
+
+
+def _p(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def from_nchw(x, c_pad=None, size=None, out=None):
+    """fp32 NCHW (cuda) -> bf16 NHWC Act, optional nearest resize to `size` (F.interpolate nearest)."""
+    assert x.is_cuda and x.dtype == torch.float32
+    x = x.contiguous()
+    n, c, h, w = x.shape
+    oh, ow = (h, w) if size is None else size
+    if out is None:
+        out = Act.empty(n, oh, ow, c, pitch=round_up(c if c_pad is None else c_pad, 8))
+    t = out.ct()
+    capi.check(capi.lib().hrv_nchw_to_nhwc(x.data_ptr(), c, h, w, ctypes.byref(t), _stream()), "nchw_to_nhwc")
+    LAUNCHES[0] += 1
+    return out
+
+
+# ----------------------------------------------------------------------------------------------- weights
+
+def pick_bk(cin):
+    cands = [64, 32] + ([16] if cin <= 16 else [])
+    pads = {bk: round_up(cin, bk) for bk in cands}
+    best = min(pads.values())
+    for bk in cands:
+        if pads[bk] <= 1.10 * best:
+            return bk
+    return cands[-1]
+
+
+def pick_bn(n_gemm):
+    n16 = round_up(n_gemm, 16)
+    if n16 <= 256:
+        return n16
+    # cost model: every N tile re-streams the A operand once (+64 ~ fixed per-tile overhead in columns)
+    best, best_cost = 256, None
+    for bn in range(256, 15, -16):
+        tiles = (n_gemm + bn - 1) // bn
+        cost = (tiles * (bn + 64), tiles * bn)
+        if best_cost is None or cost < best_cost:
+            best, best_cost = bn, cost
+    return best
+
+
+@dataclass
+class PackedConv:
+    w: torch.Tensor  # bf16 [n_pad, taps*cin_k]
+    kh: int
+    kw: int
+    off_y: int
+    off_x: int
+    bk: int
+    bn: int
+    n_gemm: int
+    cin: int
+
+
+def pack_weight(w, off, cin_total=None, interleave=None, bn=None):
+    """w: (Cout,Cin,kh,kw) fp32 cuda (already divided by sigma / transformed). Returns PackedConv.
+    interleave: a second weight of identical shape whose rows are interleaved (gamma_c, beta_c pairs)."""
+    if interleave is not None:
+        w = torch.stack([w, interleave], 1).reshape(2 * w.shape[0], *w.shape[1:])
+    cout, cin, kh, kw = w.shape
+    cin_eff = cin if cin_total is None else cin_total
+    bk = pick_bk(cin_eff)
+    cin_k = round_up(cin_eff, bk)
+    bn = pick_bn(cout) if bn is None else bn
+    n_pad = round_up(cout, bn)
+    wp = torch.zeros((n_pad, kh * kw, cin_k), dtype=torch.bfloat16, device=w.device)
+    wp[:cout, :, :cin] = w.permute(0, 2, 3, 1).reshape(cout, kh * kw, cin).to(torch.bfloat16)
+    return PackedConv(wp.reshape(n_pad, kh * kw * cin_k), kh, kw, off[0], off[1], bk, bn, cout, cin_eff)
+
+
+def s2d_weight(w, pad):
+    """Rewrite a stride-2 conv weight (Cout,Cin,k,k) with padding `pad` (k=4,pad=2 or k=3,pad=1) as the
+    2x2 stride-1 weight over the space-to-depth input with channel order (py*2+px)*Cin8 + ci, off=(1,1)."""
+    cout, cin, k, _ = w.shape
+    cin8 = round_up(cin, 8)
+    out = torch.zeros((cout, 4 * cin8, 2, 2), dtype=w.dtype, device=w.device)
+    shift = 0 if (k == 4 and pad == 2) else 1
+    assert (k, pad) in ((4, 2), (3, 1))
+    for ky in range(k):
+        ty, py = divmod(ky + shift, 2)
+        for kx in range(k):
+            tx, px = divmod(kx + shift, 2)
+            sub = py * 2 + px
+            out[:, sub * cin8:sub * cin8 + cin, ty, tx] = w[:, :, ky, kx]
+    return out
+
+
+# ----------------------------------------------------------------------------------------------- ops
+
+def conv2d(inp, pw, out, act=ACT_NONE, scale=None, shift=None, res=None, out_layout=capi.NHWC):
+    assert inp.c == pw.cin, (inp.c, pw.cin)
+    p = capi.ConvParams()
+    p.inp = inp.ct()
+    p.wpack = pw.w.data_ptr()
+    p.kh, p.kw, p.off_y, p.off_x = pw.kh, pw.kw, pw.off_y, pw.off_x
+    p.bk, p.bn, p.n_gemm = pw.bk, pw.bn, pw.n_gemm
+    if isinstance(out, Act):
+        p.out = out.ct()
+    else:  # raw fp32 NCHW torch tensor
+        n, c, h, w = out.shape
+        p.out = capi.Tensor(out.data_ptr(), n, h, w, c, c, F32)
+    p.out_layout = out_layout
+    p.epi = capi.EPI_LINEAR
+    p.act = act
+    p.scale = _p(scale)
+    p.shift = _p(shift)
+    p.res = res.ct() if res is not None else _NULL
+    p.x0 = _NULL
+    p.x1 = _NULL
+    capi.check(capi.lib().hrv_conv2d_fwd(ctypes.byref(p), _stream()), "conv2d_fwd")
+    LAUNCHES[0] += 1
+    return out
+
+
+def conv2d_spade(actv, pw, out, x0, x0_shift, x1, mean, rstd, noise, noise_scale, shift, act):
+    p = capi.ConvParams()
+    p.inp = actv.ct()
+    p.wpack = pw.w.data_ptr()
+    p.kh, p.kw, p.off_y, p.off_x = pw.kh, pw.kw, pw.off_y, pw.off_x
+    p.bk, p.bn, p.n_gemm = pw.bk, pw.bn, pw.n_gemm
+    p.out = out.ct()
+    p.out_layout = capi.NHWC
+    p.epi = capi.EPI_SPADE
+    p.act = act
+    p.scale = None
+    p.shift = _p(shift)
+    p.res = _NULL
+    p.x0 = x0.ct()
+    p.x1 = x1.ct() if x1 is not None else _NULL
+    p.x0_shift = x0_shift
+    p.mean, p.rstd, p.noise, p.noise_scale = _p(mean), _p(rstd), _p(noise), _p(noise_scale)
+    capi.check(capi.lib().hrv_conv2d_fwd(ctypes.byref(p), _stream()), "conv2d_fwd(spade)")
+    LAUNCHES[0] += 1
+    return out
+
+
+_ws = {}
+
+
+def _workspace(nbytes, device):
+    key = (device, "ws")
+    w = _ws.get(key)
+    if w is None or w.numel() < nbytes:
+        w = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _ws[key] = w
+    return w
+
+
+def instnorm_stats(x0, x0_shift, x1, h, w, noise, noise_scale, eps=1e-5):
+    n = x0.n
+    c = x0.c + (x1.c if x1 is not None else 0)
+    mean = torch.empty((n, c), dtype=torch.float32, device=x0.buf.device)
+    rstd = torch.empty_like(mean)
+    ws = _workspace(n * c * 16, x0.buf.device)
+    t0 = x0.ct()
+    t1 = x1.ct() if x1 is not None else _NULL
+    capi.check(capi.lib().hrv_instnorm_stats(ctypes.byref(t0), x0_shift, ctypes.byref(t1), h, w, _p(noise), _p(noise_scale),
+                                             eps, mean.data_ptr(), rstd.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
+               "instnorm_stats")
+    LAUNCHES[0] += 3
+    return mean, rstd
+
+
+def instnorm_apply(x, mean, rstd, act, out=None):
+    out = x if out is None else out
+    tx, ty = x.ct(), out.ct()
+    capi.check(capi.lib().hrv_instnorm_apply(ctypes.byref(tx), mean.data_ptr(), rstd.data_ptr(), act, ctypes.byref(ty), _stream()),
+               "instnorm_apply")
+    LAUNCHES[0] += 1
+    return out
+
+
+def space_to_depth(x):
+    out = Act.empty(x.n, (x.h + 1) // 2, (x.w + 1) // 2, 4 * round_up(x.c, 8))
+    tx, ty = x.ct(), out.ct()
+    capi.check(capi.lib().hrv_space_to_depth(ctypes.byref(tx), ctypes.byref(ty), _stream()), "space_to_depth")
+    LAUNCHES[0] += 1
+    return out
+
+
+def avgpool3s2(x):
+    out = Act.empty(x.n, (x.h - 1) // 2 + 1, (x.w - 1) // 2 + 1, x.c, pitch=x.pitch if x.c0 == 0 else None)
+    tx, ty = x.ct(), out.ct()
+    capi.check(capi.lib().hrv_avgpool3s2(ctypes.byref(tx), ctypes.byref(ty), _stream()), "avgpool3s2")
+    LAUNCHES[0] += 1
+    return out
+
+
+def bilinear_up2_add(a, b, out):
+    ta, to = a.ct(), out.ct()
+    tb = b.ct() if b is not None else _NULL
+    capi.check(capi.lib().hrv_bilinear_up2_add(ctypes.byref(ta), ctypes.byref(tb), ctypes.byref(to), _stream()), "bilinear_up2_add")
+    LAUNCHES[0] += 1
+    return out
+
+
+_lin = {}
+
+
+def linspace_table(n, device):
+    """torch.linspace(-1, 1, n) — the reference's base-grid values (networks.py:162-163), built on the CPU exactly as
+    the reference does, cached on the device."""
+    key = (n, str(device))
+    if key not in _lin:
+        _lin[key] = torch.linspace(-1.0, 1.0, n).to(device)
+    return _lin[key]
+
+
+def flow_warp(flow_lo, src, dst, want_flow_up=True, want_idx=False):
+    """flow_lo: fp32 (N,h,w,2) cuda contiguous. Returns (flow_up fp32 (N,2h,2w,2) | None, idx int32 | None)."""
+    n, hl, wl, _ = flow_lo.shape
+    H, W = 2 * hl, 2 * wl
+    assert dst.h == H and dst.w == W
+    dev = flow_lo.device
+    flow_up = torch.empty((n, H, W, 2), dtype=torch.float32, device=dev) if want_flow_up else None
+    idx = torch.empty((n, H, W, 2), dtype=torch.int32, device=dev) if want_idx else None
+    ts, td = src.ct(), dst.ct()
+    capi.check(capi.lib().hrv_flow_warp(flow_lo.data_ptr(), linspace_table(W, dev).data_ptr(), linspace_table(H, dev).data_ptr(),
+                                        ctypes.byref(ts), ctypes.byref(td), _p(flow_up), _p(idx), _stream()), "flow_warp")
+    LAUNCHES[0] += 1
+    return flow_up, idx

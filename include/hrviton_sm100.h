@@ -1,0 +1,138 @@
+/* hrviton_sm100.h — C-ABI of libhrviton_sm100.so (B200 / sm_100a only).
+ *
+ * The reference (sangyun884/HR-VITON) has no FFI layer: its seam is the Python module surface of
+ * networks.py / network_generator.py, whose arithmetic is delegated to ATen/cuDNN ops.  Each entry
+ * point below replaces the ATen op(s) the reference calls at the cited file:line; the Python drop-in
+ * modules at the repo root (networks.py, network_generator.py) bind them through ctypes
+ * (hr-viton_b200/capi.py).  See INTEGRATION.md for the reference-side binding.
+ *
+ * Conventions: every pointer is a DEVICE pointer owned by the caller; activations are NHWC
+ * ("pixel-major") with a channel pitch; kernels are enqueued on the given stream and never allocate
+ * or synchronise; every function returns 0 on success or a negative hrv_status, text via
+ * hrv_last_error() (thread-local).  There is no CPU fallback.
+ */
+#ifndef HRVITON_SM100_H_
+#define HRVITON_SM100_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* hrv_stream; /* cudaStream_t */
+
+enum hrv_status { HRV_OK = 0, HRV_EINVAL = -1, HRV_ECUDA = -2, HRV_EUNSUPPORTED = -3 };
+enum hrv_dtype { HRV_BF16 = 0, HRV_F32 = 1 };
+enum hrv_act { HRV_ACT_NONE = 0, HRV_ACT_RELU = 1, HRV_ACT_LRELU02 = 2, HRV_ACT_TANH = 3 };
+enum hrv_layout { HRV_NHWC = 0, HRV_NCHW = 1 };
+enum hrv_epilogue { HRV_EPI_LINEAR = 0, HRV_EPI_SPADE = 1 };
+
+/* NHWC view: element (n,y,x,c) lives at ptr + (((n*h + y)*w + x)*pitch + c) elements.
+ * For tensors read through TMA (conv inputs): bf16, ptr 16-byte aligned, pitch % 8 == 0. */
+typedef struct hrv_tensor {
+  void* ptr;
+  int32_t n, h, w, c;
+  int32_t pitch;
+  int32_t dtype; /* hrv_dtype */
+} hrv_tensor;
+
+/* One 2-D convolution as an implicit GEMM on tcgen05 tensor cores (bf16 in, fp32 accumulate in TMEM).
+ * Replaces nn.Conv2d forward at networks.py:60-93,178-192 ; network_generator.py:97-99,132-135,184-201,
+ * 263-272 and, with HRV_EPI_SPADE, the whole SPADENorm tail `normalized*(1+gamma)+beta` + LeakyReLU
+ * (network_generator.py:115-121,170-171) fused into the gamma/beta convolution.
+ *
+ *   out[n,y,x,:] = epilogue( sum_{ky,kx,ci} in[n, y+ky-off_y, x+kx-off_x, ci] * W[:,ky,kx,ci] )
+ *
+ * (stride-1 taps; stride-2 convolutions are expressed on a space-to-depth input, see hrv_space_to_depth).
+ * Out-of-range input pixels and channels read as zero (TMA OOB fill).
+ *
+ * wpack: bf16 [n_pad][kh*kw][cin_k], cin_k = ceil(in.c/bk)*bk, n_pad = ceil(n_gemm/bn)*bn, zero padded.
+ *
+ * LINEAR epilogue:  v = acc*scale[j] + shift[j] (+ res[n,y,x,j]);  out = act(v)            (j < cout)
+ * SPADE  epilogue:  GEMM column 2c = gamma_c, 2c+1 = beta_c (n_gemm = 2*C);  xs = x0|x1 concat source,
+ *                   v = ((xs + noise[n,y,x]*noise_scale[c]) - mean[n,c]) * rstd[n,c]
+ *                       * (1 + acc[2c] + shift[2c]) + (acc[2c+1] + shift[2c+1]);  out[c] = act(v)
+ *                   x0 may be half resolution (x0_shift=1: nearest x2 up-sampling folded into the index,
+ *                   network_generator.py:203,226-242); x1 supplies channels [x0.c, x0.c+x1.c) (the torch.cat).
+ */
+typedef struct hrv_conv_params {
+  hrv_tensor in;
+  const void* wpack;
+  int32_t kh, kw, off_y, off_x;
+  int32_t bk;     /* K chunk in elements: 64, 32 or 16 (=> TMA/UMMA swizzle 128B/64B/32B) */
+  int32_t bn;     /* GEMM N tile: multiple of 16, 16..256 */
+  int32_t n_gemm; /* GEMM N (cout, or 2*C for SPADE) */
+  hrv_tensor out; /* n,h,w = output extent; dtype bf16|f32 */
+  int32_t out_layout; /* hrv_layout; NCHW only with f32 */
+  int32_t epi;    /* hrv_epilogue */
+  int32_t act;    /* hrv_act */
+  const float* scale; /* [n_gemm] or NULL (=1) */
+  const float* shift; /* [n_gemm] or NULL (=0) */
+  hrv_tensor res;     /* optional residual (ptr NULL = none), same n,h,w as out */
+  hrv_tensor x0, x1;  /* SPADE sources (x1.ptr may be NULL) */
+  int32_t x0_shift;
+  const float* mean;  /* [N][C] */
+  const float* rstd;  /* [N][C] */
+  const float* noise; /* [N][H][W] or NULL */
+  const float* noise_scale; /* [C] or NULL */
+} hrv_conv_params;
+
+int hrv_conv2d_fwd(const hrv_conv_params* p, hrv_stream stream);
+
+/* Per-(n,c) InstanceNorm statistics of  v = src(c) + noise[n,y,x]*noise_scale[c]  over the h*w pixels of
+ * the (virtual) tensor  cat(up2^x0_shift(x0), x1)  — nn.InstanceNorm2d(affine=False) statistics
+ * (network_generator.py:86,110; biased variance, eps inside the sqrt) without materialising the sum,
+ * the up-sampling or the concatenation.  h,w = statistics extent.  workspace: 2*N*C doubles, zeroed by
+ * the call.  Writes mean[N][C], rstd[N][C]. */
+int hrv_instnorm_stats(const hrv_tensor* x0, int32_t x0_shift, const hrv_tensor* x1, int32_t h, int32_t w,
+                       const float* noise, const float* noise_scale, float eps,
+                       float* mean, float* rstd, void* workspace, size_t workspace_bytes, hrv_stream stream);
+
+/* y = act((x - mean[n,c]) * rstd[n,c]) elementwise on an NHWC bf16 tensor (InstanceNorm + LeakyReLU of the
+ * discriminators, network_generator.py:269-270,427; networks.py:366-386). In place allowed. */
+int hrv_instnorm_apply(const hrv_tensor* x, const float* mean, const float* rstd, int32_t act,
+                       const hrv_tensor* y, hrv_stream stream);
+
+/* fp32 NCHW -> bf16 NHWC with nearest resampling to (dst.h, dst.w): src index = floor(dst*in/out)
+ * (F.interpolate(mode='nearest'), network_generator.py:164,222) and zero fill of dst channels >= C.
+ * src: [n][c][src_h][src_w] fp32 contiguous. */
+int hrv_nchw_to_nhwc(const float* src, int32_t c, int32_t src_h, int32_t src_w, const hrv_tensor* dst, hrv_stream stream);
+
+/* bf16|f32 NHWC view -> fp32 NCHW contiguous [n][c][h][w]. */
+int hrv_nhwc_to_nchw(const hrv_tensor* src, float* dst, hrv_stream stream);
+
+/* Space-to-depth by 2 with zero fill of odd edges: dst[n,Y,X,(py*2+px)*src.c + ci] = src[n,2Y+py,2X+px,ci];
+ * dst.h = ceil(src.h/2), dst.w = ceil(src.w/2), dst.c >= 4*src.c (extra channels zeroed). Turns the
+ * stride-2 convolutions (networks.py:185; network_generator.py:263-269; networks.py:360-372) into stride-1
+ * 2x2 implicit GEMMs. */
+int hrv_space_to_depth(const hrv_tensor* src, const hrv_tensor* dst, hrv_stream stream);
+
+/* F.avg_pool2d(3, stride 2, pad 1, count_include_pad=False) on NHWC bf16 (network_generator.py:302,
+ * networks.py:320). dst.h = (src.h-1)/2+1. */
+int hrv_avgpool3s2(const hrv_tensor* src, const hrv_tensor* dst, hrv_stream stream);
+
+/* dst = bilinear_up2(a) (+ b), align_corners=False (F.interpolate / nn.Upsample, networks.py:130,181).
+ * a: (n,h,w,c) bf16; b (optional, ptr NULL = none) and dst: (n,2h,2w,c) bf16. */
+int hrv_bilinear_up2_add(const hrv_tensor* a, const hrv_tensor* b, const hrv_tensor* dst, hrv_stream stream);
+
+/* The appearance-flow warp (networks.py:133-135,147-152,161-168) in one kernel:
+ *   flow_up = bilinear_up2(flow_lo)                      (fp32 [n][H][W][2], written to flow_up if non-NULL)
+ *   g = flow_up / ((W/2-1)/2, (H/2-1)/2) + (lin_x[x], lin_y[y])      (correctly rounded fp32 division)
+ *   ix = clamp(((g.x+1)*src.w-1)/2, 0, src.w-1)  (grid_sample, bilinear, border, align_corners=False)
+ *   dst[n,y,x,:] = 4-tap lerp of src around (floor(ix), floor(iy))
+ * flow_lo: fp32 [n][H/2][W/2][2]; lin_x/lin_y: torch.linspace(-1,1,W|H) tables; src: bf16|f32 NHWC (n,H,W,c);
+ * dst: bf16|f32 NHWC view (n,H,W,c).  idx_out (optional): int32 [n][H][W][2] = (x0,y0) gather indices. */
+int hrv_flow_warp(const float* flow_lo, const float* lin_x, const float* lin_y, const hrv_tensor* src,
+                  const hrv_tensor* dst, float* flow_up, int32_t* idx_out, hrv_stream stream);
+
+/* Library / device introspection. */
+const char* hrv_last_error(void);
+int hrv_version(void);
+int hrv_device_sm_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HRVITON_SM100_H_ */

@@ -1,0 +1,227 @@
+"""GPU parity tests of every C-ABI kernel against CPU restatements (torch-CPU fp32 conv substrate and the
+numpy index formulas of oracle/hrviton_oracle.py).  All calls go through the C-ABI (hrviton_b200.ops -> ctypes)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "oracle"))
+import hrviton_oracle as orc  # noqa: E402
+from hrviton_b200 import capi, ops, synth  # noqa: E402
+from hrviton_b200.ops import Act  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def bf16r(t):
+    return t.to(torch.bfloat16).float()
+
+
+def rel_err(got, ref):
+    got = got.detach().float().cpu()
+    ref = ref.detach().float().cpu()
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    return float((got - ref).abs().max() / (ref.abs().max() + 1e-6))
+
+
+def run_conv(n, cin, cout, h, w, k, pad, *, act=0, bias=True, scale=False, res=False, seed=0, out_fp32_nchw=False,
+             in_pitch=None, stride=1):
+    x = bf16r(synth.normalish((n, cin, h, w), seed, "x"))
+    wt = bf16r(synth.normalish((cout, cin, k, k), seed, "w", (1.0 / (cin * k * k)) ** 0.5))
+    b = synth.normalish((cout,), seed, "b", 0.1) if bias else None
+    sc = synth.uniform((cout,), seed, "s", 0.5, 1.5) if scale else None
+    ref = F.conv2d(x, wt, None, stride=stride, padding=pad)
+    if sc is not None:
+        ref = ref * sc[None, :, None, None]
+    if b is not None:
+        ref = ref + b[None, :, None, None]
+    oh, ow = ref.shape[2:]
+    r = bf16r(synth.normalish((n, cout, oh, ow), seed, "r")) if res else None
+    if r is not None:
+        ref = ref + r
+    ref = {0: lambda t: t, 1: torch.relu, 2: lambda t: F.leaky_relu(t, 0.2), 3: torch.tanh}[act](ref)
+
+    xa = ops.from_nchw(x.to(DEV), c_pad=in_pitch)
+    if stride == 2:
+        xa = ops.space_to_depth(xa)
+        pw = ops.pack_weight(ops.s2d_weight(wt.to(DEV), pad), (1, 1), cin_total=xa.c)
+    else:
+        pw = ops.pack_weight(wt.to(DEV), (pad, pad))
+    ra = ops.from_nchw(r.to(DEV)) if r is not None else None
+    dsc = sc.to(DEV) if sc is not None else None
+    dsh = b.to(DEV) if b is not None else None
+    if out_fp32_nchw:
+        out = torch.empty((n, cout, oh, ow), dtype=torch.float32, device=DEV)
+        ops.conv2d(xa, pw, out, act=act, scale=dsc, shift=dsh, res=ra, out_layout=capi.NCHW)
+        got = out
+    else:
+        oa = Act.empty(n, oh, ow, cout, zero=True)
+        ops.conv2d(xa, pw, oa, act=act, scale=dsc, shift=dsh, res=ra)
+        got = oa.to_nchw()
+    torch.cuda.synchronize()
+    return rel_err(got, ref)
+
+
+CONV_CASES = [
+    # n, cin, cout, h, w, k, pad, kwargs
+    (2, 64, 64, 16, 16, 3, 1, {}),
+    (1, 128, 160, 32, 24, 3, 1, dict(act=2)),
+    (1, 80, 32, 64, 48, 3, 1, {}),
+    (2, 7, 128, 32, 24, 3, 1, dict(act=1)),
+    (1, 9, 16, 16, 12, 3, 1, {}),
+    (2, 96, 384, 16, 12, 1, 0, {}),
+    (3, 1040, 1024, 8, 6, 3, 1, {}),
+    (1, 256, 1, 17, 13, 4, 2, dict(out_fp32_nchw=True)),
+    (2, 10, 64, 33, 25, 4, 2, dict(stride=2, act=2)),
+    (2, 64, 128, 33, 25, 4, 2, dict(stride=2, bias=False)),
+    (1, 16, 96, 64, 48, 3, 1, dict(stride=2, bias=False)),
+    (1, 4, 96, 32, 24, 3, 1, dict(stride=2, bias=False)),
+    (2, 96, 96, 32, 24, 3, 1, dict(act=1, scale=True, res=True)),
+    (1, 32, 3, 64, 48, 3, 1, dict(act=3, out_fp32_nchw=True)),
+    (1, 768, 2, 16, 12, 3, 1, dict(out_fp32_nchw=True)),
+    (2, 128, 160, 256, 192, 3, 1, dict(act=2)),  # 768 tiles: persistent loop, phase wrap, TMEM double buffering
+    (1, 144, 64, 128, 96, 3, 1, {}),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=lambda c: "n%d_%dto%d_%dx%d_k%dp%d_%s" % (c[0], c[1], c[2], c[3], c[4], c[5], c[6], "_".join("%s%s" % kv for kv in c[7].items())))
+def test_conv(case):
+    n, cin, cout, h, w, k, pad, kw = case
+    err = run_conv(n, cin, cout, h, w, k, pad, **kw)
+    print('conv rel err', case, err)
+    assert err < 1e-2, err
+
+
+def test_conv_channel_slices():
+    """Input read through a channel-slice view (pitch > c), output written into a slice of a wider buffer
+    (this is how torch.cat is eliminated)."""
+    n, h, w = 1, 16, 12
+    x = bf16r(synth.normalish((n, 96, h, w), 3, "x"))
+    wt = bf16r(synth.normalish((64, 32, 3, 3), 3, "w", 0.06))
+    ref = F.conv2d(x[:, 32:64], wt, None, padding=1)
+    xa = ops.from_nchw(x.to(DEV))
+    big = Act.empty(n, h, w, 128, zero=True)
+    ops.conv2d(xa.slice(32, 32), ops.pack_weight(wt.to(DEV), (1, 1)), big.slice(64, 64))
+    got = big.to_nchw()
+    torch.cuda.synchronize()
+    assert rel_err(got[:, 64:], ref) < 1e-2
+    assert float(got[:, :64].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("shift,with_x1,cx0", [(0, False, 64), (1, True, 64), (1, True, 1024), (0, True, 32)])
+def test_conv_spade(shift, with_x1, cx0):
+    n, h, w = 2, 32, 24
+    if cx0 == 1024:
+        n, h, w = 1, 16, 12
+    cx1 = 16 if with_x1 else 0
+    C = cx0 + cx1
+    seed = 5
+    actv = bf16r(synth.normalish((n, 128, h, w), seed, "actv").abs())
+    wg = bf16r(synth.normalish((C, 128, 3, 3), seed, "wg", 0.03))
+    wb = bf16r(synth.normalish((C, 128, 3, 3), seed, "wb", 0.03))
+    bg = synth.normalish((C,), seed, "bg", 0.1)
+    bb = synth.normalish((C,), seed, "bb", 0.1)
+    x0 = bf16r(synth.normalish((n, cx0, h >> shift, w >> shift), seed, "x0"))
+    x1 = bf16r(synth.normalish((n, cx1, h, w), seed, "x1")) if with_x1 else None
+    noise = synth.spade_noise(n, h, w, seed, 0)
+    ns = synth.normalish((C,), seed, "ns", 0.1)
+    xs = F.interpolate(x0, scale_factor=2, mode="nearest") if shift else x0
+    if x1 is not None:
+        xs = torch.cat([xs, x1], 1)
+    xn = xs + noise[:, None] * ns[None, :, None, None]
+    m = xn.mean((2, 3), keepdim=True)
+    v = xn.var((2, 3), unbiased=False, keepdim=True)
+    normalized = (xn - m) / torch.sqrt(v + 1e-5)
+    gamma = F.conv2d(actv, wg, bg, padding=1)
+    beta = F.conv2d(actv, wb, bb, padding=1)
+    ref = F.leaky_relu(normalized * (1 + gamma) + beta, 0.2)
+
+    a_actv = ops.from_nchw(actv.to(DEV))
+    a_x0 = ops.from_nchw(x0.to(DEV))
+    a_x1 = ops.from_nchw(x1.to(DEV)) if x1 is not None else None
+    d_noise, d_ns = noise.to(DEV).contiguous(), ns.to(DEV)
+    mean, rstd = ops.instnorm_stats(a_x0, shift, a_x1, h, w, d_noise, d_ns)
+    torch.cuda.synchronize()
+    assert rel_err(mean, m[:, :, 0, 0]) < 2e-3 or float((mean.cpu() - m[:, :, 0, 0]).abs().max()) < 2e-3
+    assert rel_err(rstd, 1.0 / torch.sqrt(v + 1e-5)[:, :, 0, 0]) < 2e-3
+    pw = ops.pack_weight(wg.to(DEV), (1, 1), interleave=wb.to(DEV))
+    shift_vec = torch.stack([bg, bb], 1).reshape(-1).to(DEV)
+    out = Act.empty(n, h, w, C, zero=True)
+    ops.conv2d_spade(a_actv, pw, out, a_x0, shift, a_x1, mean, rstd, d_noise, d_ns, shift_vec, ops.ACT_LRELU)
+    got = out.to_nchw()
+    torch.cuda.synchronize()
+    assert rel_err(got, ref) < 1.5e-2
+
+
+def test_instnorm_apply():
+    x = bf16r(synth.normalish((2, 128, 17, 13), 7, "x", 2.0, 0.3))
+    ref = F.leaky_relu(F.instance_norm(x, eps=1e-5), 0.2)
+    a = ops.from_nchw(x.to(DEV))
+    mean, rstd = ops.instnorm_stats(a, 0, None, 17, 13, None, None)
+    ops.instnorm_apply(a, mean, rstd, ops.ACT_LRELU)
+    assert rel_err(a.to_nchw(), ref) < 1e-2
+
+
+def test_layout_and_nearest():
+    x = synth.uniform((2, 9, 32, 24), 8, "x")
+    for size in [(32, 24), (16, 12), (8, 6), (2, 1), (4, 3)]:
+        a = ops.from_nchw(x.to(DEV), size=size)
+        ref = bf16r(F.interpolate(x, size=size, mode="nearest"))
+        got = a.to_nchw()
+        assert float((got.cpu() - ref).abs().max()) == 0.0
+        assert float(a.buf[..., 9:].abs().max()) == 0.0
+
+
+def test_space_to_depth_and_avgpool():
+    x = bf16r(synth.uniform((2, 16, 17, 13), 9, "x"))
+    a = ops.from_nchw(x.to(DEV))
+    s = ops.space_to_depth(a).to_nchw().cpu()
+    xp = F.pad(x, (0, 1, 0, 1))
+    for py in range(2):
+        for px in range(2):
+            sub = py * 2 + px
+            assert float((s[:, sub * 16:(sub + 1) * 16] - xp[:, :, py::2, px::2]).abs().max()) == 0.0
+    p = ops.avgpool3s2(a).to_nchw()
+    ref = F.avg_pool2d(x, 3, stride=2, padding=1, count_include_pad=False)
+    assert rel_err(p, ref) < 1e-2
+    assert rel_err(p, torch.from_numpy(orc.np_avgpool3s2(x.numpy()))) < 1e-2
+
+
+def test_bilinear_up2_add():
+    a = bf16r(synth.uniform((2, 24, 8, 6), 10, "a"))
+    b = bf16r(synth.uniform((2, 24, 16, 12), 10, "b"))
+    ref = torch.from_numpy(orc.np_bilinear_up2(a.numpy())) + b
+    out = Act.empty(2, 16, 12, 24)
+    ops.bilinear_up2_add(ops.from_nchw(a.to(DEV)), ops.from_nchw(b.to(DEV)), out)
+    assert rel_err(out.to_nchw(), ref) < 1e-2
+
+
+@pytest.mark.parametrize("c,src_fp32", [(384, False), (4, True), (8, False)])
+def test_flow_warp_bit_exact(c, src_fp32):
+    """Gather indices and the up-sampled flow must be BIT-EXACT against the numpy restatement; values within bf16."""
+    n, h, w = 2, 32, 24
+    flow = synth.normalish((n, h // 2, w // 2, 2), 12, "fl", 3.0)
+    src = synth.uniform((n, c, h, w), 12, "src")
+    src_used = src if src_fp32 else bf16r(src)
+    x0, y0, tx, ty = orc.np_flow_warp_coords(flow.numpy(), h, w, h, w)
+    ref = torch.from_numpy(orc.np_gather_bilinear(src_used.numpy(), x0, y0, tx, ty))
+    ref_flow_up = np.moveaxis(orc.np_bilinear_up2(np.moveaxis(flow.numpy(), -1, 1)), 1, -1)
+    if src_fp32:
+        sa = Act(src.permute(0, 2, 3, 1).contiguous().to(DEV))
+        dst = Act.empty(n, h, w, c, dtype=torch.float32, pitch=c)
+    else:
+        sa = ops.from_nchw(src.to(DEV))
+        dst = Act.empty(n, h, w, c)
+    flow_up, idx = ops.flow_warp(flow.to(DEV).contiguous(), sa, dst, want_idx=True)
+    torch.cuda.synchronize()
+    idx = idx.cpu().numpy()
+    assert np.array_equal(idx[..., 0], x0) and np.array_equal(idx[..., 1], y0)
+    assert np.array_equal(flow_up.cpu().numpy(), ref_flow_up)
+    got = dst.to_nchw()
+    assert rel_err(got, ref) < (1e-5 if src_fp32 else 1e-2)
+    # and against the torch substrate the reference actually calls
+    assert rel_err(got, orc.flow_warp(src_used, flow)) < (1e-4 if src_fp32 else 1e-2)
