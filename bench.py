@@ -1,0 +1,313 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the HR-VITON hot path on B200 (driver contract: see the task statement).
+
+    python bench.py --gpus 1 --steps 10 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+    python bench.py --impl reference ...      # the reference algorithm on the host CPU cores (oracle port)
+
+Prints ONE JSON line on rank 0.  Workloads (config.workload):
+  gen_fwd    SPADEGenerator inference forward, 1024x768, per-GPU batch 8, bf16 activations (BASELINE.json configs[2])
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+import types
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, W = 1024, 768
+GEN_GFLOP_PER_IMG = 1636.4  # conv FLOPs of one SPADEGenerator forward at 1024x768
+
+
+def gen_opt():
+    return types.SimpleNamespace(norm_G="spectralaliasinstance", gen_semantic_nc=7, ngf=64, num_upsampling_layers="most",
+                                 fine_height=H, fine_width=W, cuda=True)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "tf_burst": d["bf16_tflops"], "tf_sustained": d["bf16_tflops_sustained"], "src": "measured"}
+    return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_generator(device):
+    import torch
+
+    import network_generator
+    from hrviton_b200 import spade
+    torch.manual_seed(0)
+    g = network_generator.SPADEGenerator(gen_opt(), 9)
+    g.init_weights("xavier", 0.02)
+    with torch.no_grad():
+        for m in g.modules():
+            if isinstance(m, spade.SPADENorm):
+                m.noise_scale.normal_(0.0, 0.1)
+    g = g.to(device).eval()
+    with torch.no_grad():  # realistic spectral-norm u/v (a fresh module holds random vectors)
+        for m in g.modules():
+            if hasattr(m, "weight_orig"):
+                for _ in range(3):
+                    spade._sigma(m, True)
+    return g
+
+
+def synth_batch(b, device, seed):
+    import torch
+    gen = torch.Generator(device="cpu").manual_seed(seed)
+    x = torch.rand((b, 9, H, W), generator=gen) * 2 - 1
+    lab = torch.randint(0, 7, (b, H // 16, W // 16), generator=gen)
+    lab = lab.repeat_interleave(16, 1).repeat_interleave(16, 2)
+    seg = torch.zeros((b, 7, H, W)).scatter_(1, lab[:, None], 1.0)
+    return x, seg
+
+
+def cpu_baseline_gen(steps=1, warmup=0, budget_s=240.0):
+    """The reference algorithm on the host cores: the oracle port (oracle/hrviton_oracle.py — the reference is Python and
+    cannot travel to the GPU box) — SPADEGenerator forward, fp32, one 1024x768 image per step."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import hrviton_oracle as orc
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    import network_generator
+    torch.manual_seed(0)
+    m = network_generator.SPADEGenerator(gen_opt(), 9)
+    m.init_weights("xavier", 0.02)
+    sd = {k: v.detach() for k, v in m.state_dict().items()}
+    x, seg = synth_batch(1, "cpu", 1)
+    noise_fn = lambda b, hh, ww: torch.randn(b, hh, ww)
+    times = []
+    t_begin = time.time()
+    done = 0
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.time()
+            orc.spade_generator_forward(sd, x, seg, noise_fn)
+            dt = time.time() - t0
+            if i >= warmup:
+                times.append(dt)
+                done += 1
+            if time.time() - t_begin + dt > budget_s and done >= 1:
+                break
+    times.sort()
+    med = times[len(times) // 2]
+    return {"value": 1.0 / med, "unit": "images/s", "cores": cores, "kind": "port",
+            "sample": "SPADEGenerator fwd fp32, 1 image 1024x768 per step, %d timed step(s), torch %s CPU" % (len(times), torch.__version__),
+            "s_per_image": med, "steps_done": len(times)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb = cpu_baseline_gen(steps=max(1, args.steps), warmup=min(args.warmup, 1))
+    line = {"impl": "reference", "metric": "1024x768 try-on images/sec", "value": cb["value"], "unit": "images/s", "n_gpus": args.gpus,
+            "steps": cb["steps_done"], "warmup": min(args.warmup, 1), "ms_per_step": cb["s_per_image"] * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "gen_fwd: SPADEGenerator inference forward 1024x768 (reference algorithm, host CPU, 1 image per step)"},
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": cb["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=8, help="per-GPU batch")
+    ap.add_argument("--workload", default="gen_fwd", choices=["gen_fwd"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dump-profile", default="", help="write the per-launch CUDA-event profile of one step as CSV")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    import hrv_loader
+    hrv_loader.load()
+    from hrviton_b200 import ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    W_ = max(3, args.warmup)
+    K, B = args.steps, args.batch
+
+    g = build_generator(dev)
+    x_h, seg_h = synth_batch(B, "cpu", 100 + rank)
+    x_h, seg_h = x_h.pin_memory(), seg_h.pin_memory()
+    x_d, seg_d = x_h.to(dev), seg_h.to(dev)
+    out_h = torch.empty((B, 3, H, W), dtype=torch.float32).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        with torch.no_grad():
+            return g(x_d, seg_d)
+
+    def step_e2e():
+        with torch.no_grad():
+            xd = x_h.to(dev, non_blocking=True)
+            sd = seg_h.to(dev, non_blocking=True)
+            out = g(xd, sd)
+            out_h.copy_(out, non_blocking=True)
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for _ in range(W_):
+        step_resident()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = ops.LAUNCHES[0]
+    ms = timed(step_resident, K)
+    launches = ops.LAUNCHES[0] - l0
+    clocks = sampler.stop() if rank == 0 else None
+    value = B * world * K / (ms / 1e3)
+
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, K)
+    e2e_value = B * world * K / (ms_e2e / 1e3)
+
+    # ---- per-kernel profile pass (CUDA events around every C-ABI launch) -> roofline of the dominant kernel
+    ops.PROFILE = []
+    torch.cuda.synchronize()
+    step_resident()
+    torch.cuda.synchronize()
+    prof = ops.PROFILE
+    ops.PROFILE = None
+    agg = {}
+    if args.dump_profile and rank == 0:
+        with open(args.dump_profile, "w") as f:
+            f.write("kind,label,ms,work,rate_T_per_s\n")
+            for kind, work, e0, e1, label in prof:
+                t = e0.elapsed_time(e1)
+                f.write("%s,%s,%.4f,%.4g,%.2f\n" % (kind, label, t, work, work / (t * 1e-3) / 1e12 if t > 0 else 0))
+    for kind, work, e0, e1, _label in prof:
+        a = agg.setdefault(kind, [0.0, 0.0, 0])
+        a[0] += work
+        a[1] += e0.elapsed_time(e1)
+        a[2] += 1
+    peaks = measured_peaks()
+    conv_flops = agg.get("conv", [0, 0, 0])[0] + agg.get("conv_spade", [0, 0, 0])[0]
+    conv_ms = agg.get("conv", [0, 0, 0])[1] + agg.get("conv_spade", [0, 0, 0])[1]
+    conv_launches = agg.get("conv", [0, 0, 0])[2] + agg.get("conv_spade", [0, 0, 0])[2]
+    achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+    roofline = {"kernel": "conv_igemm_kernel (tcgen05 implicit-GEMM conv, all %d launches of one step)" % conv_launches,
+                "bound": "tensor", "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                "frac": achieved / peaks["tf_sustained"], "traffic": None, "peak_source": peaks["src"] + " (bf16 sustained)",
+                "avg_launch_ms": conv_ms / max(1, conv_launches), "algorithmic_gflop_per_launch": conv_flops / 1e9 / max(1, conv_launches)}
+    total_prof_ms = sum(a[1] for a in agg.values())
+    breakdown = {k: {"ms": round(a[1], 3), "launches": a[2], "share": round(a[1] / total_prof_ms, 4)} for k, a in agg.items()}
+    if "instnorm_stats" in agg:
+        a = agg["instnorm_stats"]
+        breakdown["instnorm_stats"]["achieved_GBps"] = round(a[0] / (a[1] * 1e-3) / 1e9, 1)
+        breakdown["instnorm_stats"]["frac_of_hbm_peak"] = round(a[0] / (a[1] * 1e-3) / 1e9 / peaks["hbm_gbs"], 4)
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_baseline = cpu_baseline_gen(steps=1, warmup=0)
+        cpu_baseline = {k: cpu_baseline[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {"metric": "1024x768 try-on images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W_,
+                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+                "data": "synthetic",
+                "config": {"workload": "gen_fwd: SPADEGenerator inference forward (fwd only — backward not built yet), 1024x768, bf16 activations, fp32 accumulate",
+                           "per_gpu_batch": B, "global_batch": B * world, "parallelism": "dp%d" % world,
+                           "l2": "activations per step (>10 GB) exceed the 126 MB L2; no explicit flush",
+                           "weights": "xavier(0.02) random init, noise_scale~N(0,0.1)"},
+                "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": ms_e2e / K,
+                        "h2d_bytes_per_step": int(x_h.numel() * 4 + seg_h.numel() * 4), "d2h_bytes_per_step": int(out_h.numel() * 4)},
+                "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernel_breakdown": breakdown,
+                "model_tflops": GEN_GFLOP_PER_IMG * value / 1e3}
+        if cpu_baseline is not None:
+            line["cpu_baseline"] = cpu_baseline
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -7,7 +7,29 @@ import torch
 from . import capi
 from .capi import ACT_LRELU, ACT_NONE, ACT_RELU, ACT_TANH, BF16, F32  # noqa: F401
 
-LAUNCHES = [0]  # count of C-ABI kernel-launching calls (bench.py reads this for `gpu_launches`)
+LAUNCHES = [0]  # count of kernel launches issued through the C-ABI (bench.py reads this for `gpu_launches`)
+PROFILE = None  # bench.py sets this to a list; every C-ABI call then appends (kind, work, start_event, end_event)
+
+
+class _Timed:
+    """Brackets one C-ABI call with CUDA events on the launching stream when profiling is on (bench.py roofline)."""
+
+    def __init__(self, kind, work, launches=1, label=""):
+        self.kind, self.work, self.launches, self.label = kind, work, launches, label
+
+    def __enter__(self):
+        LAUNCHES[0] += self.launches
+        if PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None:
+            self.e1.record()
+            PROFILE.append((self.kind, self.work, self.e0, self.e1, self.label))
+        return False
 
 
 def _stream():
@@ -115,9 +137,10 @@ class PackedConv:
     bn: int
     n_gemm: int
     cin: int
+    flops_per_pixel: float = 0.0  # algorithmic 2*Cin*Cout*kh*kw of the ORIGINAL convolution (unpadded, pre-s2d)
 
 
-def pack_weight(w, off, cin_total=None, interleave=None, bn=None):
+def pack_weight(w, off, cin_total=None, interleave=None, bn=None, flops_per_pixel=None):
     """w: (Cout,Cin,kh,kw) fp32 cuda (already divided by sigma / transformed). Returns PackedConv.
     interleave: a second weight of identical shape whose rows are interleaved (gamma_c, beta_c pairs)."""
     if interleave is not None:
@@ -130,7 +153,8 @@ def pack_weight(w, off, cin_total=None, interleave=None, bn=None):
     n_pad = round_up(cout, bn)
     wp = torch.zeros((n_pad, kh * kw, cin_k), dtype=torch.bfloat16, device=w.device)
     wp[:cout, :, :cin] = w.permute(0, 2, 3, 1).reshape(cout, kh * kw, cin).to(torch.bfloat16)
-    return PackedConv(wp.reshape(n_pad, kh * kw * cin_k), kh, kw, off[0], off[1], bk, bn, cout, cin_eff)
+    fpp = 2.0 * cin * cout * kh * kw if flops_per_pixel is None else flops_per_pixel
+    return PackedConv(wp.reshape(n_pad, kh * kw * cin_k), kh, kw, off[0], off[1], bk, bn, cout, cin_eff, fpp)
 
 
 def s2d_weight(w, pad):
@@ -148,6 +172,12 @@ def s2d_weight(w, pad):
             sub = py * 2 + px
             out[:, sub * cin8:sub * cin8 + cin, ty, tx] = w[:, :, ky, kx]
     return out
+
+
+def pack_s2d(w, pad):
+    """PackedConv of a stride-2 convolution expressed on the space-to-depth input (algorithmic FLOPs of the original)."""
+    cout, cin, k, _ = w.shape
+    return pack_weight(s2d_weight(w, pad), (1, 1), flops_per_pixel=2.0 * cin * cout * k * k)
 
 
 # ----------------------------------------------------------------------------------------------- ops
@@ -172,8 +202,9 @@ def conv2d(inp, pw, out, act=ACT_NONE, scale=None, shift=None, res=None, out_lay
     p.res = res.ct() if res is not None else _NULL
     p.x0 = _NULL
     p.x1 = _NULL
-    capi.check(capi.lib().hrv_conv2d_fwd(ctypes.byref(p), _stream()), "conv2d_fwd")
-    LAUNCHES[0] += 1
+    with _Timed("conv", pw.flops_per_pixel * p.out.n * p.out.h * p.out.w,
+                label="%d->%d k%dx%d n%d %dx%d bk%d bn%d" % (inp.c, pw.n_gemm, pw.kh, pw.kw, p.out.n, p.out.h, p.out.w, pw.bk, pw.bn)):
+        capi.check(capi.lib().hrv_conv2d_fwd(ctypes.byref(p), _stream()), "conv2d_fwd")
     return out
 
 
@@ -194,8 +225,9 @@ def conv2d_spade(actv, pw, out, x0, x0_shift, x1, mean, rstd, noise, noise_scale
     p.x1 = x1.ct() if x1 is not None else _NULL
     p.x0_shift = x0_shift
     p.mean, p.rstd, p.noise, p.noise_scale = _p(mean), _p(rstd), _p(noise), _p(noise_scale)
-    capi.check(capi.lib().hrv_conv2d_fwd(ctypes.byref(p), _stream()), "conv2d_fwd(spade)")
-    LAUNCHES[0] += 1
+    with _Timed("conv_spade", pw.flops_per_pixel * out.n * out.h * out.w,
+                label="%d->%d k%dx%d n%d %dx%d bk%d bn%d" % (actv.c, pw.n_gemm, pw.kh, pw.kw, out.n, out.h, out.w, pw.bk, pw.bn)):
+        capi.check(capi.lib().hrv_conv2d_fwd(ctypes.byref(p), _stream()), "conv2d_fwd(spade)")
     return out
 
 
@@ -219,10 +251,11 @@ def instnorm_stats(x0, x0_shift, x1, h, w, noise, noise_scale, eps=1e-5):
     ws = _workspace(n * c * 16, x0.buf.device)
     t0 = x0.ct()
     t1 = x1.ct() if x1 is not None else _NULL
-    capi.check(capi.lib().hrv_instnorm_stats(ctypes.byref(t0), x0_shift, ctypes.byref(t1), h, w, _p(noise), _p(noise_scale),
-                                             eps, mean.data_ptr(), rstd.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
-               "instnorm_stats")
-    LAUNCHES[0] += 3
+    nbytes = n * h * w * (2.0 * c + (4.0 if noise is not None else 0.0))  # one bf16 read of every element (+ noise)
+    with _Timed("instnorm_stats", nbytes, launches=3, label="c%d n%d %dx%d shift%d" % (c, n, h, w, x0_shift)):
+        capi.check(capi.lib().hrv_instnorm_stats(ctypes.byref(t0), x0_shift, ctypes.byref(t1), h, w, _p(noise), _p(noise_scale),
+                                                 eps, mean.data_ptr(), rstd.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
+                   "instnorm_stats")
     return mean, rstd
 
 

@@ -94,7 +94,11 @@ def fill_state_dict(sd, seed):
 
 def tocg_inputs(n, h, w, seed):
     """input1 = cloth(3)+mask(1); input2 = one-hot parse(13)+densepose(3)  (SURVEY §8d)."""
-    cloth = uniform((n, 3, h, w), seed, "cloth")
+    # a smooth "garment": low-resolution random field, bilinearly enlarged (exact fp32 lerps), plus faint texture —
+    # white-noise cloth would turn a 0.03-pixel flow difference into an O(0.1) colour difference
+    import torch.nn.functional as F
+    coarse = uniform((n, 3, max(2, h // 16), max(2, w // 16)), seed, "cloth")
+    cloth = F.interpolate(coarse, size=(h, w), mode="bilinear", align_corners=True) * 0.9 + uniform((n, 3, h, w), seed, "cloth_tex") * 0.05
     mask = (labels((n, h, w), 2, seed, "cmask", block=32)[:, None]).float()
     parse = one_hot(labels((n, h, w), 13, seed, "parse", block=16), 13)
     dense = uniform((n, 3, h, w), seed, "dense")

@@ -77,7 +77,7 @@ def main():
                      **{"flow%d" % i: f for i, f in enumerate(flows)})
 
         if want("gen"):
-            for tag, (n, h, w) in {"gen_256x128_b1": (1, 256, 128), "gen_128x256_b2": (2, 128, 256)}.items():
+            for tag, (n, h, w) in {"gen_512x384_b1": (1, 512, 384), "gen_256x256_b2": (2, 256, 256)}.items():
                 seed = 23
                 opt = gen_opt(h, w)
                 m = ref_gen.SPADEGenerator(opt, 9).eval()
@@ -98,7 +98,7 @@ def main():
                     out = m(x, seg)
                 finally:
                     torch.randn = real_randn
-                save(tag, seed=seed, shape=[n, h, w], out=out, n_noise=counter[0])
+                save(tag, seed=seed, shape=[n, h, w], out=out.half(), n_noise=counter[0])  # fp16 storage: 5e-4 abs on (-1,1)
 
         if want("gend"):
             seed = 31

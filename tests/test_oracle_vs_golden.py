@@ -31,7 +31,7 @@ def test_tocg(name):
     assert maxdiff(wcm, g["warped_cm"]) < 1e-4
 
 
-@pytest.mark.parametrize("name", ["gen_256x128_b1", "gen_128x256_b2"])
+@pytest.mark.parametrize("name", ["gen_512x384_b1", "gen_256x256_b2"])
 def test_gen(name):
     g = load_golden(name)
     n, h, w = [int(v) for v in g["shape"]]
@@ -48,7 +48,7 @@ def test_gen(name):
     with torch.no_grad():
         out = orc.spade_generator_forward(sd, x, seg, noise_fn)
     assert cnt[0] == int(g["n_noise"]) == 23
-    assert maxdiff(out, g["out"]) < 1e-4
+    assert maxdiff(out, g["out"].astype(np.float32)) < 1e-3  # fixture stored as fp16
 
 
 def test_gend():
