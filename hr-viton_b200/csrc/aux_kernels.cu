@@ -30,16 +30,28 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 __device__ __forceinline__ uint4 ldg16(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 
 // ------------------------------------------------------------------------------------------------ IN statistics
-// grid (chunks, N); thread = (pixel lane, channel group of 8); registers accumulate fp32 over the lane's pixels,
-// then fp64 shared/global atomics (one global atomic per channel per block).
+// grid (chunks, N); thread = (pixel lane pl, channel group g of 8).  Each thread accumulates fp32 partial sums over its
+// pixels (4 independent 16-byte loads in flight), partials meet in shared memory (one slot per thread, no atomics),
+// then one fp64 global atomic per channel per block.
+struct StatsSrc {
+  const __nv_bfloat16* p0;
+  const __nv_bfloat16* p1;
+  const float* noise;
+  long long pitch0, pitch1;
+  int W, W0, sh, from0;
+};
+__device__ __forceinline__ void stats_load(const StatsSrc& S, long long p, uint4& v, float& nz) {
+  const int y = (int)(p / S.W), x = (int)(p - (long long)y * S.W);
+  const __nv_bfloat16* src = S.from0 ? S.p0 + ((long long)(y >> S.sh) * S.W0 + (x >> S.sh)) * S.pitch0 : S.p1 + p * S.pitch1;
+  v = ldg16(src);
+  nz = S.noise ? __ldg(S.noise + p) : 0.f;
+}
 __global__ void __launch_bounds__(256) instnorm_stats_kernel(View x0, int x0_shift, View x1, int H, int W, int G, int PL,
                                                             int chunk, const float* __restrict__ noise,
                                                             const float* __restrict__ ns, double* __restrict__ acc) {
-  extern __shared__ double sh[];  // [G*8][2]
+  extern __shared__ float shf[];  // [PL][C][2]
   const int n = blockIdx.y;
   const int C = G * 8;
-  for (int i = threadIdx.x; i < C * 2; i += blockDim.x) sh[i] = 0.0;
-  __syncthreads();
   const int g = threadIdx.x % G;
   const int pl = threadIdx.x / G;
   if (pl < PL) {
@@ -51,31 +63,57 @@ __global__ void __launch_bounds__(256) instnorm_stats_kernel(View x0, int x0_shi
     float s[8], q[8], nsv[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { s[i] = 0.f; q[i] = 0.f; nsv[i] = ns ? __ldg(ns + c0 + i) : 0.f; }
-    const bool from0 = c0 < x0.c;
-    const int W0 = W >> x0_shift, H0 = H >> x0_shift;
-    for (long long p = p_begin + pl; p < p_end; p += PL) {
-      const int y = (int)(p / W), x = (int)(p - (long long)y * W);
-      const __nv_bfloat16* src =
-          from0 ? reinterpret_cast<const __nv_bfloat16*>(x0.ptr) + (((long long)n * H0 + (y >> x0_shift)) * W0 + (x >> x0_shift)) * x0.pitch + c0
-                : reinterpret_cast<const __nv_bfloat16*>(x1.ptr) + (((long long)n * H + y) * W + x) * x1.pitch + (c0 - x0.c);
-      float f[8];
-      unpack8(ldg16(src), f);
-      const float nz = noise ? __ldg(noise + (long long)n * HW + p) : 0.f;
+    StatsSrc S;
+    S.from0 = c0 < x0.c;
+    S.sh = x0_shift; S.W = W; S.W0 = W >> x0_shift;
+    S.pitch0 = x0.pitch; S.pitch1 = x1.pitch;
+    S.p0 = reinterpret_cast<const __nv_bfloat16*>(x0.ptr) + (long long)n * (H >> x0_shift) * S.W0 * x0.pitch + c0;
+    S.p1 = reinterpret_cast<const __nv_bfloat16*>(x1.ptr) + (long long)n * HW * x1.pitch + (c0 - x0.c);
+    S.noise = noise ? noise + (long long)n * HW : nullptr;
+    long long p = p_begin + pl;
+    for (; p + 3LL * PL < p_end; p += 4LL * PL) {
+      uint4 v[4];
+      float nz[4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float v = fmaf(nz, nsv[i], f[i]);
-        s[i] += v;
-        q[i] = fmaf(v, v, q[i]);
+      for (int u = 0; u < 4; ++u) stats_load(S, p + (long long)u * PL, v[u], nz[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float f[8];
+        unpack8(v[u], f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float t = fmaf(nz[u], nsv[i], f[i]);
+          s[i] += t;
+          q[i] = fmaf(t, t, q[i]);
+        }
       }
     }
+    for (; p < p_end; p += PL) {
+      uint4 v;
+      float nz, f[8];
+      stats_load(S, p, v, nz);
+      unpack8(v, f);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      atomicAdd(&sh[(c0 + i) * 2], (double)s[i]);
-      atomicAdd(&sh[(c0 + i) * 2 + 1], (double)q[i]);
+      for (int i = 0; i < 8; ++i) {
+        const float t = fmaf(nz, nsv[i], f[i]);
+        s[i] += t;
+        q[i] = fmaf(t, t, q[i]);
+      }
     }
+    float* dst = shf + ((long long)pl * C + c0) * 2;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { dst[2 * i] = s[i]; dst[2 * i + 1] = q[i]; }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < C * 2; i += blockDim.x) atomicAdd(&acc[(long long)n * C * 2 + i], sh[i]);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    double S1 = 0.0, S2 = 0.0;
+    for (int l = 0; l < PL; ++l) {
+      S1 += (double)shf[((long long)l * C + c) * 2];
+      S2 += (double)shf[((long long)l * C + c) * 2 + 1];
+    }
+    atomicAdd(&acc[((long long)n * C + c) * 2], S1);
+    atomicAdd(&acc[((long long)n * C + c) * 2 + 1], S2);
+  }
 }
 
 __global__ void instnorm_finalize_kernel(const double* __restrict__ acc, int NC, double inv_hw, float eps,
@@ -359,7 +397,7 @@ extern "C" int hrv_instnorm_stats(const hrv_tensor* x0, int32_t x0_shift, const 
   const long long min_chunk = (long long)PL * 16;
   if (chunk < min_chunk) chunk = min_chunk;
   const unsigned gx = (unsigned)((HW + chunk - 1) / chunk);
-  instnorm_stats_kernel<<<dim3(gx, N), 256, (size_t)C * 2 * sizeof(double), st>>>(mk(x0), x0_shift, mk(has1 ? x1 : nullptr), h, w, G, PL,
+  instnorm_stats_kernel<<<dim3(gx, N), 256, (size_t)PL * C * 2 * sizeof(float), st>>>(mk(x0), x0_shift, mk(has1 ? x1 : nullptr), h, w, G, PL,
                                                                                  (int)chunk, noise, noise_scale, (double*)workspace);
   if ((rc = launch_ok("instnorm_stats"))) return rc;
   instnorm_finalize_kernel<<<blocks_for(N * C, 256), 256, 0, st>>>((const double*)workspace, N * C, 1.0 / (double)HW, eps, mean, rstd);

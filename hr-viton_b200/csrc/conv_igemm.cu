@@ -7,7 +7,7 @@
 //   B operand:  one TMA 2-D box {BK, BN} of the packed weights [n_pad][taps*cin_k] (K-major).
 //   MMA:        tcgen05.mma.cta_group::1.kind::f16, M=128 x N=BN x K=16, bf16 inputs, fp32 accumulators in TMEM.
 //   Pipeline:   persistent CTAs (one per SM); warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
-//               warps 4-7 = epilogue.  smem ring of `stages` (A,B) buffers with full/empty mbarriers; TMEM holds two
+//               warps 4.. = kEpiWG epilogue warpgroups (16-column chunks round-robin; loads issued before the TMEM read).  smem ring of `stages` (A,B) buffers with full/empty mbarriers; TMEM holds two
 //               accumulator buffers so the epilogue of tile i overlaps the MMAs of tile i+1.
 //   Epilogues:  LINEAR  out = act(acc*scale + shift (+ residual))      (bias / folded BatchNorm / residual / tanh)
 //               SPADE   out = act((x + noise*ns - mean)*rstd*(1+gamma) + beta), gamma/beta = interleaved GEMM columns:
@@ -19,8 +19,9 @@
 
 namespace hrv {
 
-constexpr int kMaxStages = 8;
-constexpr int kThreads = 256;
+constexpr int kMaxStages = 32;
+constexpr int kEpiWG = 4;                       // epilogue warpgroups: each handles every kEpiWG-th 16-column chunk
+constexpr int kThreads = 128 + 128 * kEpiWG;  // warps 0-3: TMA / MMA / TMEM-alloc / spare; then the epilogue warpgroups
 
 struct alignas(64) ConvArgs {
   CUtensorMap tmA;
@@ -86,7 +87,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_tfull(i), 1);
-      mbar_init(bar_tempty(i), 128);
+      mbar_init(bar_tempty(i), 128 * kEpiWG);
     }
     fence_mbar_init();
   } else if (warp == 2) {
@@ -154,8 +155,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
       umma_commit(bar_tfull(acc));  // accumulator complete -> epilogue
     }
   } else if (warp >= 4) {
-    // ===================================================== epilogue (4 warps, one TMEM lane = one pixel per thread)
-    const int q = warp & 3;
+    // ===================================================== epilogue (one TMEM lane = one pixel per thread)
+    const int q = warp & 3;             // TMEM lane quarter this warp may access
+    const int wg = (warp - 4) >> 2;     // epilogue warpgroup: owns 16-column chunks wg, wg+kEpiWG, ...
     const int r = q * 32 + lane;
     const int tw_mask = (1 << a.tw_log) - 1, th_mask = (1 << a.th_log) - 1;
     uint32_t tcount = 0;
@@ -182,7 +184,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
       if (a.epi == 0) {
         // ---------------- LINEAR
         const int store_c = (a.out_dtype == 0 && a.out_layout == 0) ? ((a.out_c + 7) & ~7) : a.out_c;
-        for (int col = 0; col < a.BN; col += 16) {
+        for (int col = wg * 16; col < a.BN; col += 16 * kEpiWG) {
           uint32_t v[16];
           __syncwarp();
           tmem_ld16(taddr + col, v);
@@ -194,13 +196,27 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
             const int jg = j0 + g * 8;
             if (jg >= store_c) break;
             float f[8];
+            if (jg + 8 <= a.n_gemm) {  // vector path (scale/shift arrays are 16-byte aligned torch allocations)
+              float sc[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f}, sh[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+              if (a.scale) {
+                *reinterpret_cast<float4*>(sc) = __ldg(reinterpret_cast<const float4*>(a.scale + jg));
+                *reinterpret_cast<float4*>(sc + 4) = __ldg(reinterpret_cast<const float4*>(a.scale + jg) + 1);
+              }
+              if (a.shift) {
+                *reinterpret_cast<float4*>(sh) = __ldg(reinterpret_cast<const float4*>(a.shift + jg));
+                *reinterpret_cast<float4*>(sh + 4) = __ldg(reinterpret_cast<const float4*>(a.shift + jg) + 1);
+              }
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int j = jg + i;
-              const bool in = j < a.n_gemm;
-              const float sc = in ? (a.scale ? __ldg(a.scale + j) : 1.f) : 0.f;
-              const float sh = (in && a.shift) ? __ldg(a.shift + j) : 0.f;
-              f[i] = fmaf(__uint_as_float(v[g * 8 + i]), sc, sh);
+              for (int i = 0; i < 8; ++i) f[i] = fmaf(__uint_as_float(v[g * 8 + i]), sc[i], sh[i]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int j = jg + i;
+                const bool in = j < a.n_gemm;
+                const float sc = in ? (a.scale ? __ldg(a.scale + j) : 1.f) : 0.f;
+                const float sh = (in && a.shift) ? __ldg(a.shift + j) : 0.f;
+                f[i] = fmaf(__uint_as_float(v[g * 8 + i]), sc, sh);
+              }
             }
             if (a.res) {
               if (a.res_dtype == 0) {
@@ -241,33 +257,53 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
         const int sh0 = a.x0_shift;
         const long long pix0 = ((long long)n * (a.Hout >> sh0) + (y >> sh0)) * (a.Wout >> sh0) + (x >> sh0);
         const float nz = (valid && a.noise) ? __ldg(a.noise + pix) : 0.f;
-        for (int col = 0; col < a.BN; col += 16) {
+        for (int col = wg * 16; col < a.BN; col += 16 * kEpiWG) {
+          const int c0 = (n_base + col) >> 1;
+          const bool live = valid && c0 < a.C_mod;
+          // issue every global load of this chunk before touching TMEM so their latencies overlap the tcgen05.ld
+          uint4 xv = make_uint4(0, 0, 0, 0);
+          float mu[8], rs[8], nsv[8], sh[16];
+          if (live) {
+            const __nv_bfloat16* xp = (c0 < a.x0_c) ? (a.x0 + pix0 * a.x0_pitch + c0)
+                                                     : (a.x1 + pix * a.x1_pitch + (c0 - a.x0_c));
+            xv = __ldg(reinterpret_cast<const uint4*>(xp));
+            const float4* mp = reinterpret_cast<const float4*>(a.mean + (long long)n * a.C_mod + c0);
+            const float4* rp = reinterpret_cast<const float4*>(a.rstd + (long long)n * a.C_mod + c0);
+            *reinterpret_cast<float4*>(mu) = __ldg(mp);
+            *reinterpret_cast<float4*>(mu + 4) = __ldg(mp + 1);
+            *reinterpret_cast<float4*>(rs) = __ldg(rp);
+            *reinterpret_cast<float4*>(rs + 4) = __ldg(rp + 1);
+            if (a.noise_scale) {
+              const float4* np_ = reinterpret_cast<const float4*>(a.noise_scale + c0);
+              *reinterpret_cast<float4*>(nsv) = __ldg(np_);
+              *reinterpret_cast<float4*>(nsv + 4) = __ldg(np_ + 1);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) nsv[i] = 0.f;
+            }
+            if (a.shift) {
+              const float4* sp = reinterpret_cast<const float4*>(a.shift + 2 * c0);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(sh + 4 * i) = __ldg(sp + i);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) sh[i] = 0.f;
+            }
+          }
           uint32_t v[16];
           __syncwarp();
           tmem_ld16(taddr + col, v);
           tmem_wait_ld();
-          const int c0 = (n_base + col) >> 1;
-          if (!valid || c0 >= a.C_mod) continue;
-          const __nv_bfloat16* xp = (c0 < a.x0_c) ? (a.x0 + pix0 * a.x0_pitch + c0)
-                                                   : (a.x1 + pix * a.x1_pitch + (c0 - a.x0_c));
-          const uint4 xv = __ldg(reinterpret_cast<const uint4*>(xp));
-          float xs[8] = {bf16_lo(xv.x), bf16_hi(xv.x), bf16_lo(xv.y), bf16_hi(xv.y),
-                         bf16_lo(xv.z), bf16_hi(xv.z), bf16_lo(xv.w), bf16_hi(xv.w)};
+          if (!live) continue;
+          const float xs[8] = {bf16_lo(xv.x), bf16_hi(xv.x), bf16_lo(xv.y), bf16_hi(xv.y),
+                               bf16_lo(xv.z), bf16_hi(xv.z), bf16_lo(xv.w), bf16_hi(xv.w)};
           float o[8];
-          const float* mp = a.mean + (long long)n * a.C_mod + c0;
-          const float* rp = a.rstd + (long long)n * a.C_mod + c0;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const int c = c0 + i;
-            float xval = xs[i];
-            if (a.noise_scale) xval = fmaf(nz, __ldg(a.noise_scale + c), xval);
-            float gm = __uint_as_float(v[2 * i]);
-            float bt = __uint_as_float(v[2 * i + 1]);
-            if (a.shift) {
-              gm += __ldg(a.shift + 2 * c);
-              bt += __ldg(a.shift + 2 * c + 1);
-            }
-            const float xn = (xval - __ldg(mp + i)) * __ldg(rp + i);
+            const float xval = fmaf(nz, nsv[i], xs[i]);
+            const float gm = __uint_as_float(v[2 * i]) + sh[2 * i];
+            const float bt = __uint_as_float(v[2 * i + 1]) + sh[2 * i + 1];
+            const float xn = (xval - mu[i]) * rs[i];
             o[i] = apply_act(fmaf(xn, 1.f + gm, bt), a.act);
           }
           uint4 ov;

@@ -124,14 +124,13 @@ class SPADENorm(nn.Module):
         raise RuntimeError("SPADENorm is fused into SPADEResBlock.forward in hrviton_b200; call the block")
 
     def packed(self):
-        """(shared PackedConv, shared bias, gamma|beta interleaved PackedConv, interleaved bias, noise_scale)."""
+        """(gamma|beta interleaved PackedConv, interleaved bias, noise_scale); conv_shared is packed by the block, which
+        merges the conv_shared of all its norms into one GEMM over the same segmentation map."""
         if self.kind != "instance":
             raise NotImplementedError("only 'aliasinstance' SPADE normalisation has a kernel (the reference's configuration)")
-        cs = self.conv_shared[0]
-        shared = ops.pack_weight(cs.weight.detach(), (1, 1))
         gb = ops.pack_weight(self.conv_gamma.weight.detach(), (1, 1), interleave=self.conv_beta.weight.detach())
         gb_bias = torch.stack([self.conv_gamma.bias.detach(), self.conv_beta.bias.detach()], 1).reshape(-1).float().contiguous()
-        return shared, cs.bias.detach().float().contiguous(), gb, gb_bias, self.noise_scale.detach().float().contiguous()
+        return gb, gb_bias, self.noise_scale.detach().float().contiguous()
 
 
 class SPADEResBlock(nn.Module):
@@ -165,7 +164,11 @@ class SPADEResBlock(nn.Module):
     def _packed(self):
         key = (_param_key(self), self.training)
         if self._cache_key != key or self.training:
-            c = {"n0": self.norm_0.packed(), "n1": self.norm_1.packed(),
+            norms = ([self.norm_s] if self.learned_shortcut else []) + [self.norm_0, self.norm_1]
+            # one conv_shared GEMM for all norms of the block: N = 128 * len(norms), same seg operand read once
+            c = {"shared": ops.pack_weight(torch.cat([m.conv_shared[0].weight.detach() for m in norms], 0), (1, 1)),
+                 "shared_b": torch.cat([m.conv_shared[0].bias.detach() for m in norms], 0).float().contiguous(),
+                 "n0": self.norm_0.packed(), "n1": self.norm_1.packed(),
                  "c0": ops.pack_weight(_conv_weight(self.conv_0, self.training), (1, 1)),
                  "c1": ops.pack_weight(_conv_weight(self.conv_1, self.training), (1, 1)),
                  "b0": self.conv_0.bias.detach().float().contiguous(), "b1": self.conv_1.bias.detach().float().contiguous()}
@@ -175,12 +178,12 @@ class SPADEResBlock(nn.Module):
             self._cache, self._cache_key = c, (_param_key(self), self.training)
         return self._cache
 
-    def _spade(self, pk, seg, x0, x0_shift, x1, noise, act):
-        """act(InstanceNorm(x + noise*ns) * (1 + gamma(seg)) + beta(seg)) for the virtual tensor cat(up(x0), x1)."""
-        shared, shared_b, gb, gb_b, ns = pk
-        n, h, w = seg.n, seg.h, seg.w
+    @staticmethod
+    def _spade(pk, actv, x0, x0_shift, x1, noise, act):
+        """act(InstanceNorm(x + noise*ns) * (1 + gamma(actv)) + beta(actv)) for the virtual tensor cat(up(x0), x1)."""
+        gb, gb_b, ns = pk
+        n, h, w = actv.n, actv.h, actv.w
         mean, rstd = ops.instnorm_stats(x0, x0_shift, x1, h, w, noise, ns)
-        actv = ops.conv2d(seg, shared, Act.empty(n, h, w, 128), act=ACT_RELU, shift=shared_b)
         c = x0.c + (x1.c if x1 is not None else 0)
         return ops.conv2d_spade(actv, gb, Act.empty(n, h, w, c), x0, x0_shift, x1, mean, rstd, noise, ns, gb_b, act)
 
@@ -189,15 +192,18 @@ class SPADEResBlock(nn.Module):
         noise_fn(n,h,w) -> fp32 (n,h,w) cuda; draw order norm_s, norm_0, norm_1 (network_generator.py:157-171)."""
         p = self._packed()
         n, h, w = seg.n, seg.h, seg.w
+        actv = ops.conv2d(seg, p["shared"], Act.empty(n, h, w, p["shared"].n_gemm), act=ACT_RELU, shift=p["shared_b"])
+        k = 0
         if self.learned_shortcut:
-            hs = self._spade(p["ns"], seg, x0, x0_shift, x1, noise_fn(n, h, w), ACT_NONE)
+            hs = self._spade(p["ns"], actv.slice(0, 128), x0, x0_shift, x1, noise_fn(n, h, w), ACT_NONE)
             x_s = ops.conv2d(hs, p["cs"], Act.empty(n, h, w, p["cs"].n_gemm))
+            k = 128
         else:
             assert x0_shift == 0 and x1 is None
             x_s = x0
-        h0 = self._spade(p["n0"], seg, x0, x0_shift, x1, noise_fn(n, h, w), ACT_LRELU)
+        h0 = self._spade(p["n0"], actv.slice(k, 128), x0, x0_shift, x1, noise_fn(n, h, w), ACT_LRELU)
         dx = ops.conv2d(h0, p["c0"], Act.empty(n, h, w, p["c0"].n_gemm), shift=p["b0"])
-        h1 = self._spade(p["n1"], seg, dx, 0, None, noise_fn(n, h, w), ACT_LRELU)
+        h1 = self._spade(p["n1"], actv.slice(k + 128, 128), dx, 0, None, noise_fn(n, h, w), ACT_LRELU)
         return ops.conv2d(h1, p["c1"], Act.empty(n, h, w, p["c1"].n_gemm), shift=p["b1"], res=x_s, act=out_act)
 
     def forward(self, x, seg, misalign_mask=None):
