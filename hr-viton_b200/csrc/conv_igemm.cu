@@ -6,6 +6,12 @@
 //               offset; TMA zero-fills out-of-range pixels (= the convolution's zero padding) and channels.
 //   B operand:  one TMA 2-D box {BK, BN} of the packed weights [n_pad][taps*cin_k] (K-major).
 //   MMA:        tcgen05.mma.cta_group::1.kind::f16, M=128 x N=BN x K=16, bf16 inputs, fp32 accumulators in TMEM.
+//   Halo mode:  (default for images >= 12 rows) the tile is 16 rows x 8 pixels of one image; ONE TMA box of
+//               (16+KH-1) x (8+KW-1) pixels per channel chunk lands in shared memory and every tap is a *shifted view* of
+//               it: the UMMA descriptor starts at row (ky*(8+KW-1)+kx) with SBO = (8+KW-1) rows.  tcgen05 applies the
+//               128B/64B/32B swizzle on absolute shared-memory address bits (probed on B200: tools/umma_halo_probe.cu),
+//               exactly as TMA wrote it, so unaligned starts are legal.  KH*KW-fold less L2->smem traffic and TMA issue
+//               than tap-by-tap loading.  Weights ride a second ring with `tpb` taps per TMA (3-D box).
 //   Pipeline:   persistent CTAs (one per SM); warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
 //               warps 4.. = kEpiWG epilogue warpgroups (16-column chunks round-robin; loads issued before the TMEM read).  smem ring of `stages` (A,B) buffers with full/empty mbarriers; TMEM holds two
 //               accumulator buffers so the epilogue of tile i overlaps the MMAs of tile i+1.
@@ -14,6 +20,8 @@
 //                       the SPADE modulation never leaves registers (network_generator.py:115-121,170-171).
 //
 // Replaces nn.Conv2d at networks.py:60-93,178-192 and network_generator.py:97-99,132-135,184-201,263-272.
+#include <stdlib.h>
+
 #include "hrv_host.h"
 #include "hrv_ptx.cuh"
 
@@ -30,7 +38,8 @@ struct alignas(64) ConvArgs {
   int tw_log, th_log;
   int tiles_x, tiles_y, tiles_img, tiles_n;
   int KH, KW, off_y, off_x, chunks;
-  int BN, stages, n_gemm;
+  int BN, stages, n_gemm, nacc;  // nacc = TMEM accumulator stages = min(8, 512/BN)
+  int halo, tpb, sb_stages, a_stage_bytes, a_stage_bytes_tx, b_stage_bytes, line_pitch;  // halo mode: `stages` A-halo stages + sb_stages weight stages
   int epi, act;
   const float* scale;
   const float* shift;
@@ -59,23 +68,29 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
-  // control block: [0,1024): barriers + tmem pointer ; stages follow, each 1024-aligned
+  // control block [0,2048): four barrier arrays of kMaxStages (A full/empty, B full/empty), TMEM barriers, TMEM pointer.
+  // Tap-by-tap mode uses only the "A" ring (each stage = A box + B box); halo mode uses both rings.
   auto bar_full = [&](int s) { return base + 8u * s; };
-  auto bar_empty = [&](int s) { return base + 8u * (kMaxStages + s); };
-  auto bar_tfull = [&](int i) { return base + 8u * (2 * kMaxStages + i); };
-  auto bar_tempty = [&](int i) { return base + 8u * (2 * kMaxStages + 2 + i); };
-  const uint32_t tmem_slot = base + 8u * (2 * kMaxStages + 4);
+  auto bar_empty = [&](int s) { return base + 256u + 8u * s; };
+  auto bar_bfull = [&](int s) { return base + 512u + 8u * s; };
+  auto bar_bempty = [&](int s) { return base + 768u + 8u * s; };
+  auto bar_tfull = [&](int i) { return base + 1024u + 8u * i; };
+  auto bar_tempty = [&](int i) { return base + 1088u + 8u * i; };
+  const uint32_t tmem_slot = base + 1152u;
+  const uint32_t NACC = (uint32_t)a.nacc;
   const uint32_t b_bytes = (uint32_t)a.BN * ROW_BYTES;
-  const uint32_t stage_bytes = A_BYTES + ((b_bytes + 1023u) & ~1023u);
-  const uint32_t stage0 = base + 1024u;
+  const uint32_t stage_bytes = a.halo ? (uint32_t)a.a_stage_bytes : A_BYTES + ((b_bytes + 1023u) & ~1023u);
+  const uint32_t stage0 = base + 2048u;
+  const uint32_t bstage0 = stage0 + (uint32_t)a.stages * stage_bytes;  // halo mode: weight ring after the halo ring
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int S = a.stages;
+  const int SB = a.sb_stages;
   const int KT = a.KH * a.KW * a.chunks;
   const int total_tiles = a.tiles_n * a.tiles_x * a.tiles_y * a.tiles_img;
   uint32_t tmem_cols = 32;
-  while (tmem_cols < 2u * a.BN) tmem_cols <<= 1;
+  while (tmem_cols < (uint32_t)a.nacc * a.BN) tmem_cols <<= 1;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&a.tmA);
@@ -85,7 +100,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
       mbar_init(bar_full(s), 1);
       mbar_init(bar_empty(s), 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int s = 0; s < SB; ++s) {
+      mbar_init(bar_bfull(s), 1);
+      mbar_init(bar_bempty(s), 1);
+    }
+    for (int i = 0; i < a.nacc; ++i) {
       mbar_init(bar_tfull(i), 1);
       mbar_init(bar_tempty(i), 128 * kEpiWG);
     }
@@ -99,60 +118,170 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
 
-  if (warp == 0 && lane == 0) {
-    // ===================================================== TMA producer
-    uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int nt = tile % a.tiles_n;
-      int mt = tile / a.tiles_n;
-      const int tx = mt % a.tiles_x;
-      mt /= a.tiles_x;
-      const int ty = mt % a.tiles_y;
-      const int ti = mt / a.tiles_y;
-      const int x0 = (tx << a.tw_log) - a.off_x;
-      const int y0 = (ty << a.th_log) - a.off_y;
-      const int n0 = ti << (7 - a.tw_log - a.th_log);
-      int kcol = 0;
-      for (int ky = 0; ky < a.KH; ++ky) {
-        for (int kx = 0; kx < a.KW; ++kx) {
-          for (int kc = 0; kc < a.chunks; ++kc, ++it, kcol += BK) {
-            const int s = it % S;
-            const uint32_t ph = (it / S) & 1u;
-            mbar_wait(bar_empty(s), ph ^ 1u);
-            mbar_arrive_expect_tx(bar_full(s), A_BYTES + b_bytes);
-            const uint32_t sa = stage0 + s * stage_bytes;
-            tma_load_4d(sa, &a.tmA, bar_full(s), kc * BK, x0 + kx, y0 + ky, n0);
-            tma_load_2d(sa + A_BYTES, &a.tmB, bar_full(s), kcol, nt * a.BN);
+  if (warp == 0) {
+    // ===================================================== TMA producer (whole warp, warp-uniform; one elected lane issues)
+    // All ring cursors (stage index, phase bit, smem address) advance incrementally: no divisions in the hot loops.
+    const int taps = a.KH * a.KW;
+    if (a.halo) {
+      // halo ring cursor (runs ahead of the weight ring by up to S chunks, possibly into later tiles)
+      int as = 0, akc = 0, atile = blockIdx.x;
+      uint32_t aph = 0, a_addr = stage0, a_issued = 0, a_fed = 0;
+      int ax0 = 0, ay0 = 0, an0 = 0;
+      bool a_decode = true;
+      const uint32_t my_tiles = (uint32_t)((total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1);
+      const uint32_t my_chunks = my_tiles * (uint32_t)a.chunks;
+      int bs = 0;
+      uint32_t bph = 0, b_addr = bstage0;
+      const uint32_t b_tx = (uint32_t)a.tpb * b_bytes;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile % a.tiles_n;
+        for (int kc = 0; kc < a.chunks; ++kc, ++a_fed) {
+          uint32_t want = a_fed + (uint32_t)S;
+          if (want > my_chunks) want = my_chunks;
+          while (a_issued < want) {
+            if (a_decode) {
+              int mta = atile / a.tiles_n;
+              const int txa = mta % a.tiles_x;
+              mta /= a.tiles_x;
+              const int tya = mta % a.tiles_y;
+              an0 = mta / a.tiles_y;
+              ax0 = (txa << a.tw_log) - a.off_x;
+              ay0 = (tya << a.th_log) - a.off_y;
+              a_decode = false;
+            }
+            mbar_wait(bar_empty(as), aph ^ 1u);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(bar_full(as), (uint32_t)a.a_stage_bytes_tx);
+              tma_load_4d(a_addr, &a.tmA, bar_full(as), akc * BK, ax0, ay0, an0);
+            }
+            __syncwarp();
+            ++a_issued;
+            a_addr += stage_bytes;
+            if (++as == S) { as = 0; aph ^= 1u; a_addr = stage0; }
+            if (++akc == a.chunks) { akc = 0; atile += gridDim.x; a_decode = true; }
+          }
+          for (int t0 = 0; t0 < taps; t0 += a.tpb) {
+            mbar_wait(bar_bempty(bs), bph ^ 1u);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(bar_bfull(bs), b_tx);
+              tma_load_3d(b_addr, &a.tmB, bar_bfull(bs), kc * BK, nt * a.BN, t0);
+            }
+            __syncwarp();
+            b_addr += (uint32_t)a.b_stage_bytes;
+            if (++bs == SB) { bs = 0; bph ^= 1u; b_addr = bstage0; }
+          }
+        }
+      }
+    } else {
+      int st = 0;
+      uint32_t ph = 0, sa = stage0;
+      const uint32_t tx_bytes = A_BYTES + b_bytes;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile % a.tiles_n;
+        int mt = tile / a.tiles_n;
+        const int tx = mt % a.tiles_x;
+        mt /= a.tiles_x;
+        const int ty = mt % a.tiles_y;
+        const int ti = mt / a.tiles_y;
+        const int x0 = (tx << a.tw_log) - a.off_x;
+        const int y0 = (ty << a.th_log) - a.off_y;
+        const int n0 = ti << (7 - a.tw_log - a.th_log);
+        int tap = 0;
+        for (int ky = 0; ky < a.KH; ++ky) {
+          for (int kx = 0; kx < a.KW; ++kx, ++tap) {
+            for (int kc = 0; kc < a.chunks; ++kc) {
+              mbar_wait(bar_empty(st), ph ^ 1u);
+              if (elect_one()) {
+                mbar_arrive_expect_tx(bar_full(st), tx_bytes);
+                tma_load_4d(sa, &a.tmA, bar_full(st), kc * BK, x0 + kx, y0 + ky, n0);
+                tma_load_3d(sa + A_BYTES, &a.tmB, bar_full(st), kc * BK, nt * a.BN, tap);
+              }
+              __syncwarp();
+              sa += stage_bytes;
+              if (++st == S) { st = 0; ph ^= 1u; sa = stage0; }
+            }
           }
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ===================================================== MMA issuer (single thread)
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer (whole warp, warp-uniform; one elected lane issues)
     const uint32_t idesc = make_idesc_bf16(128, (uint32_t)a.BN);
-    uint32_t it = 0, tcount = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
-      const uint32_t acc = tcount & 1u;
-      const uint32_t aph = (tcount >> 1) & 1u;
-      mbar_wait(bar_tempty(acc), aph ^ 1u);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * (uint32_t)a.BN;
-      for (int k = 0; k < KT; ++k, ++it) {
-        const int s = it % S;
-        const uint32_t ph = (it / S) & 1u;
-        mbar_wait(bar_full(s), ph);
+    const int taps = a.KH * a.KW;
+    const uint64_t db_hi = make_smem_desc(0, SBO, LAYOUT);
+    uint32_t acc = 0, acc_ph = 0;  // TMEM accumulator buffer and its phase
+    if (a.halo) {
+      // descriptors = constant high words | (address >> 4); taps advance by adding row offsets
+      const uint64_t da_hi = make_smem_desc(0, (uint32_t)a.line_pitch * ROW_BYTES, LAYOUT);  // SBO = one output row of 8 px
+      const uint32_t row_wrap = (uint32_t)(a.line_pitch - a.KW) * ROW_BYTES;
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0, a_addr = stage0, b_addr = bstage0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(bar_tempty(acc), acc_ph ^ 1u);
         tc_fence_after();
-        const uint32_t sa = stage0 + s * stage_bytes;
-        const uint32_t sb = sa + A_BYTES;
+        const uint32_t d_tmem = tmem_base + acc * (uint32_t)a.BN;
+        uint32_t accumulate = 0;
+        for (int kc = 0; kc < a.chunks; ++kc) {
+          mbar_wait(bar_full(as), aph);
+          uint32_t sa_tap = a_addr;  // shifted view of the halo tile, advanced tap by tap
+          int kx = 0;
+          for (int t0 = 0; t0 < taps; t0 += a.tpb) {
+            mbar_wait(bar_bfull(bs), bph);
+            tc_fence_after();
+            uint32_t sb_tap = b_addr;
+            for (int t = 0; t < a.tpb; ++t) {
+              const uint64_t da = da_hi | (uint64_t)((sa_tap & 0x3FFFFu) >> 4);
+              const uint64_t db = db_hi | (uint64_t)((sb_tap & 0x3FFFFu) >> 4);
+              if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < BK / 16; ++kk) {
-          const uint64_t da = make_smem_desc(sa + kk * 32, SBO, LAYOUT);
-          const uint64_t db = make_smem_desc(sb + kk * 32, SBO, LAYOUT);
-          umma_f16(d_tmem, da, db, idesc, (uint32_t)((k | kk) != 0));
+                for (int kk = 0; kk < BK / 16; ++kk) umma_f16(d_tmem, da + 2u * kk, db + 2u * kk, idesc, (kk == 0) ? accumulate : 1u);
+              }
+              __syncwarp();
+              accumulate = 1;
+              sb_tap += b_bytes;
+              sa_tap += ROW_BYTES;
+              if (++kx == a.KW) { kx = 0; sa_tap += row_wrap; }
+            }
+            if (elect_one()) umma_commit(bar_bempty(bs));
+            __syncwarp();
+            b_addr += (uint32_t)a.b_stage_bytes;
+            if (++bs == SB) { bs = 0; bph ^= 1u; b_addr = bstage0; }
+          }
+          if (elect_one()) umma_commit(bar_empty(as));
+          __syncwarp();
+          a_addr += stage_bytes;
+          if (++as == S) { as = 0; aph ^= 1u; a_addr = stage0; }
         }
-        umma_commit(bar_empty(s));  // frees this smem stage once the MMAs above have read it
+        if (elect_one()) umma_commit(bar_tfull(acc));  // accumulator complete -> epilogue
+        __syncwarp();
+        if (++acc == NACC) { acc = 0; acc_ph ^= 1u; }
       }
-      umma_commit(bar_tfull(acc));  // accumulator complete -> epilogue
+    } else {
+      const uint64_t da_hi = make_smem_desc(0, SBO, LAYOUT);
+      int st = 0;
+      uint32_t ph = 0, sa = stage0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(bar_tempty(acc), acc_ph ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * (uint32_t)a.BN;
+        for (int k = 0; k < KT; ++k) {
+          mbar_wait(bar_full(st), ph);
+          tc_fence_after();
+          const uint64_t da = da_hi | (uint64_t)((sa & 0x3FFFFu) >> 4);
+          const uint64_t db = db_hi | (uint64_t)(((sa + A_BYTES) & 0x3FFFFu) >> 4);
+          if (elect_one()) {
+#pragma unroll
+            for (int kk = 0; kk < BK / 16; ++kk) umma_f16(d_tmem, da + 2u * kk, db + 2u * kk, idesc, (uint32_t)((k | kk) != 0));
+            umma_commit(bar_empty(st));  // frees this smem stage once the MMAs above have read it
+          }
+          __syncwarp();
+          sa += stage_bytes;
+          if (++st == S) { st = 0; ph ^= 1u; sa = stage0; }
+        }
+        if (elect_one()) umma_commit(bar_tfull(acc));  // accumulator complete -> epilogue
+        __syncwarp();
+        if (++acc == NACC) { acc = 0; acc_ph ^= 1u; }
+      }
     }
   } else if (warp >= 4) {
     // ===================================================== epilogue (one TMEM lane = one pixel per thread)
@@ -160,8 +289,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
     const int wg = (warp - 4) >> 2;     // epilogue warpgroup: owns 16-column chunks wg, wg+kEpiWG, ...
     const int r = q * 32 + lane;
     const int tw_mask = (1 << a.tw_log) - 1, th_mask = (1 << a.th_log) - 1;
-    uint32_t tcount = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+    uint32_t acc = 0, aph = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int nt = tile % a.tiles_n;
       int mt = tile / a.tiles_n;
       const int tx = mt % a.tiles_x;
@@ -174,12 +303,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
       const bool valid = (x < a.Wout) && (y < a.Hout) && (n < a.Nimg);
       const long long pix = ((long long)n * a.Hout + y) * a.Wout + x;
 
-      const uint32_t acc = tcount & 1u;
-      const uint32_t aph = (tcount >> 1) & 1u;
+      const int n_base = nt * a.BN;
       mbar_wait(bar_tfull(acc), aph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)a.BN;
-      const int n_base = nt * a.BN;
 
       if (a.epi == 0) {
         // ---------------- LINEAR
@@ -315,6 +442,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
       __syncwarp();
       tc_fence_before();
       mbar_arrive(bar_tempty(acc));
+      if (++acc == NACC) { acc = 0; aph ^= 1u; }
     }
   }
 
@@ -386,8 +514,17 @@ extern "C" int hrv_conv2d_fwd(const hrv_conv_params* p, hrv_stream stream) {
   ConvArgs a;
   memset(&a, 0, sizeof(a));
   a.Nimg = out.n; a.Hout = out.h; a.Wout = out.w;
-  const int TW = pick_pow2(out.w, 128);
-  const int TH = pick_pow2(out.h, 128 / TW);
+  // Halo mode (one (16+KH-1)x(8+KW-1) box per channel chunk, taps as shifted descriptor views) whenever the image is
+  // tall enough for a 16x8 single-image tile; tap-by-tap mode (tile may span images) for the tiny pyramid levels.
+  static const char* force = getenv("HRV_CONV_HALO");
+  // Measured on B200 (tools/conv_bench.py, profiles/conv_variants_r1.txt): the halo path wins for narrow GEMMs
+  // (N <= 32: 1.3-1.45x) and for the 144..208-column SPADE gamma/beta GEMMs (+5%); tap-by-tap wins for 1x1 and N=256.
+  const bool halo_shape = (p->bn <= 32) || (p->bk == 16) || (p->bk == 64 && p->bn >= 144 && p->bn <= 208);
+  bool halo = out.h >= 12 && p->kh * p->kw > 1 && halo_shape;
+  if (force && force[0] == '0') halo = false;
+  if (force && force[0] == '1') halo = true;
+  const int TW = halo ? 8 : pick_pow2(out.w, 128);
+  const int TH = halo ? 16 : pick_pow2(out.h, 128 / TW);
   const int TN = 128 / (TW * TH);
   a.tw_log = log2i(TW); a.th_log = log2i(TH);
   a.tiles_x = (out.w + TW - 1) / TW;
@@ -397,6 +534,7 @@ extern "C" int hrv_conv2d_fwd(const hrv_conv_params* p, hrv_stream stream) {
   a.KH = p->kh; a.KW = p->kw; a.off_y = p->off_y; a.off_x = p->off_x;
   a.chunks = (in.c + p->bk - 1) / p->bk;
   a.BN = p->bn; a.n_gemm = p->n_gemm;
+  a.nacc = 512 / p->bn > 8 ? 8 : 512 / p->bn;
   a.epi = p->epi; a.act = p->act;
   a.scale = p->scale; a.shift = p->shift;
   a.out = out.ptr; a.out_pitch = out.pitch; a.out_dtype = out.dtype; a.out_layout = p->out_layout; a.out_c = out.c;
@@ -420,34 +558,65 @@ extern "C" int hrv_conv2d_fwd(const hrv_conv_params* p, hrv_stream stream) {
     return set_error(HRV_EINVAL, "conv: unknown epilogue %d", p->epi);
   }
 
-  // ---- tensor maps
+  // ---- pipeline geometry
   const int elem = 2;
+  const int taps = p->kh * p->kw;
+  const uint32_t row_bytes = p->bk * 2;
+  const uint32_t budget = 225u * 1024u - 3072u;  // 1 KB alignment slack + 2 KB control block
+  const int LP = TW + p->kw - 1, HRows = (TH + p->kh - 1) * LP;
+  int tpb = 1;
+  if (halo) {
+    a.halo = 1;
+    a.line_pitch = LP;
+    a.a_stage_bytes_tx = (int)(HRows * row_bytes);
+    a.a_stage_bytes = (int)((HRows * row_bytes + 1023u) & ~1023u);
+    static const char* env_tpb = getenv("HRV_CONV_TPB_KB");
+    const uint32_t tpb_cap = (env_tpb ? (uint32_t)atoi(env_tpb) : 80u) * 1024u;
+    for (int d = taps; d >= 1; --d)
+      if (taps % d == 0 && (uint32_t)d * p->bn * row_bytes <= tpb_cap) { tpb = d; break; }
+    a.tpb = tpb;
+    a.b_stage_bytes = (int)(((uint32_t)tpb * p->bn * row_bytes + 1023u) & ~1023u);
+    // halo ring: ~72 KB in flight (at least 3 stages), the rest of shared memory goes to the weight ring
+    int sa = (int)(72u * 1024u / (uint32_t)a.a_stage_bytes);
+    if (sa < 3) sa = 3;
+    if (sa > 16) sa = 16;
+    static const char* env_sa = getenv("HRV_CONV_SA");
+    if (env_sa) sa = atoi(env_sa);
+    while (sa > 2 && (uint32_t)sa * a.a_stage_bytes + 2u * a.b_stage_bytes > budget) --sa;
+    int sb = (int)((budget - (uint32_t)sa * a.a_stage_bytes) / (uint32_t)a.b_stage_bytes);
+    if (sb > kMaxStages) sb = kMaxStages;
+    if (sb < 2) return set_error(HRV_EINVAL, "conv: tile too large for shared memory (halo mode)");
+    a.stages = sa; a.sb_stages = sb;
+  } else {
+    a.tpb = 1;
+    const uint32_t stage_bytes = 128 * row_bytes + (((uint32_t)p->bn * row_bytes + 1023u) & ~1023u);
+    int stages = (int)(budget / stage_bytes);
+    if (stages > kMaxStages) stages = kMaxStages;
+    if (stages < 2) return set_error(HRV_EINVAL, "conv: tile too large for shared memory");
+    a.stages = stages; a.sb_stages = 0;
+  }
+  // ---- tensor maps
   const CUtensorMapSwizzle sw = p->bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (p->bk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   {
     cuuint64_t dims[4] = {(cuuint64_t)in.c, (cuuint64_t)in.w, (cuuint64_t)in.h, (cuuint64_t)in.n};
     cuuint64_t strides[3] = {(cuuint64_t)in.pitch * elem, (cuuint64_t)in.w * in.pitch * elem, (cuuint64_t)in.h * in.w * in.pitch * elem};
-    cuuint32_t box[4] = {(cuuint32_t)p->bk, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TN};
+    cuuint32_t box[4] = {(cuuint32_t)p->bk, (cuuint32_t)(halo ? LP : TW), (cuuint32_t)(halo ? TH + p->kh - 1 : TH), (cuuint32_t)TN};
     cuuint32_t es[4] = {1, 1, 1, 1};
     int rc = encode_tensor_map(&a.tmA, 4, in.ptr, dims, strides, box, es, sw);
     if (rc) return rc;
   }
   {
-    const cuuint64_t ktot = (cuuint64_t)p->kh * p->kw * a.chunks * p->bk;
-    cuuint64_t dims[2] = {ktot, (cuuint64_t)a.tiles_n * p->bn};
-    cuuint64_t strides[1] = {ktot * elem};
-    cuuint32_t box[2] = {(cuuint32_t)p->bk, (cuuint32_t)p->bn};
-    cuuint32_t es[2] = {1, 1};
-    int rc = encode_tensor_map(&a.tmB, 2, const_cast<void*>(p->wpack), dims, strides, box, es, sw);
+    // packed weights [taps][n_pad][cin_k]: a 3-D map lets one TMA fetch `tpb` taps of one (channel chunk, N tile)
+    const cuuint64_t cin_k = (cuuint64_t)a.chunks * p->bk, n_pad = (cuuint64_t)a.tiles_n * p->bn;
+    cuuint64_t dims[3] = {cin_k, n_pad, (cuuint64_t)taps};
+    cuuint64_t strides[2] = {cin_k * elem, n_pad * cin_k * elem};
+    cuuint32_t box[3] = {(cuuint32_t)p->bk, (cuuint32_t)p->bn, (cuuint32_t)tpb};
+    cuuint32_t es[3] = {1, 1, 1};
+    int rc = encode_tensor_map(&a.tmB, 3, const_cast<void*>(p->wpack), dims, strides, box, es, sw);
     if (rc) return rc;
   }
-
-  const uint32_t row_bytes = p->bk * 2;
-  const uint32_t stage_bytes = 128 * row_bytes + (((uint32_t)p->bn * row_bytes + 1023u) & ~1023u);
-  int stages = (int)((225u * 1024u - 2048u) / stage_bytes);
-  if (stages > kMaxStages) stages = kMaxStages;
-  if (stages < 2) return set_error(HRV_EINVAL, "conv: tile too large for shared memory");
-  a.stages = stages;
-  size_t smem = 2048 + (size_t)stages * stage_bytes;
+  size_t smem = 3072 + (halo ? (size_t)a.stages * a.a_stage_bytes + (size_t)a.sb_stages * a.b_stage_bytes
+                             : (size_t)a.stages * (128 * row_bytes + (((uint32_t)p->bn * row_bytes + 1023u) & ~1023u)));
   if (smem < 120 * 1024) smem = 120 * 1024;  // force one CTA per SM (TMEM: up to 512 columns per CTA)
 
   const long long total = (long long)a.tiles_n * a.tiles_x * a.tiles_y * a.tiles_img;

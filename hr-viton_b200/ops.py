@@ -128,7 +128,7 @@ def pick_bn(n_gemm):
 
 @dataclass
 class PackedConv:
-    w: torch.Tensor  # bf16 [n_pad, taps*cin_k]
+    w: torch.Tensor  # bf16 [taps, n_pad, cin_k]
     kh: int
     kw: int
     off_y: int
@@ -151,10 +151,10 @@ def pack_weight(w, off, cin_total=None, interleave=None, bn=None, flops_per_pixe
     cin_k = round_up(cin_eff, bk)
     bn = pick_bn(cout) if bn is None else bn
     n_pad = round_up(cout, bn)
-    wp = torch.zeros((n_pad, kh * kw, cin_k), dtype=torch.bfloat16, device=w.device)
-    wp[:cout, :, :cin] = w.permute(0, 2, 3, 1).reshape(cout, kh * kw, cin).to(torch.bfloat16)
+    wp = torch.zeros((kh * kw, n_pad, cin_k), dtype=torch.bfloat16, device=w.device)
+    wp[:, :cout, :cin] = w.permute(2, 3, 0, 1).reshape(kh * kw, cout, cin).to(torch.bfloat16)
     fpp = 2.0 * cin * cout * kh * kw if flops_per_pixel is None else flops_per_pixel
-    return PackedConv(wp.reshape(n_pad, kh * kw * cin_k), kh, kw, off[0], off[1], bk, bn, cout, cin_eff, fpp)
+    return PackedConv(wp, kh, kw, off[0], off[1], bk, bn, cout, cin_eff, fpp)
 
 
 def s2d_weight(w, pad):

@@ -48,7 +48,7 @@ typedef struct hrv_tensor {
  * (stride-1 taps; stride-2 convolutions are expressed on a space-to-depth input, see hrv_space_to_depth).
  * Out-of-range input pixels and channels read as zero (TMA OOB fill).
  *
- * wpack: bf16 [n_pad][kh*kw][cin_k], cin_k = ceil(in.c/bk)*bk, n_pad = ceil(n_gemm/bn)*bn, zero padded.
+ * wpack: bf16 [kh*kw][n_pad][cin_k], cin_k = ceil(in.c/bk)*bk, n_pad = ceil(n_gemm/bn)*bn, zero padded.
  *
  * LINEAR epilogue:  v = acc*scale[j] + shift[j] (+ res[n,y,x,j]);  out = act(v)            (j < cout)
  * SPADE  epilogue:  GEMM column 2c = gamma_c, 2c+1 = beta_c (n_gemm = 2*C);  xs = x0|x1 concat source,
