@@ -1,0 +1,367 @@
+"""Training path (forward + backward) of the SPADE generator and its discriminator.
+
+torch.autograd carries the graph; every node is a fused C-ABI op on pixel-major bf16 buffers:
+
+  ConvFn    y = act(conv(x, W) * 1 + b (+ res))          fwd: hrv_conv2d_fwd
+            dX  = conv(dY', flip(W)^T)                     bwd: hrv_conv2d_fwd again (dgrad IS a convolution)
+            dW  = x^T (*) dY'                              bwd: hrv_conv2d_wgrad (tcgen05) when available, else the cuDNN
+                                                                weight-gradient as a staged stand-in
+  SpadeFn   h = act(IN(cat(up(x0),x1) + noise*ns) * (1+gamma(actv)) + beta(actv))
+            fwd: hrv_instnorm_stats + hrv_conv2d_fwd(SPADE epilogue); bwd: modulation / InstanceNorm backward +
+            dgrad/wgrad of the gamma|beta GEMM.
+
+Spectral norm stays differentiable in torch (W/sigma with sigma = u.(W v), tiny weight-sized tensors), exactly as the
+reference's old-style torch.nn.utils.spectral_norm does (network_generator.py:138-143).
+"""
+import torch
+import torch.nn.functional as F
+
+from . import ops
+from .ops import ACT_LRELU, ACT_NONE, ACT_RELU, ACT_TANH, Act
+
+_PACK_DTYPE = torch.bfloat16
+
+
+def _act_grad(dy, y, act):
+    """dL/dv from dL/dy for y = act(v), using only y (all our activations are invertible in sign / value)."""
+    if act == ACT_NONE:
+        return dy
+    if act == ACT_RELU:
+        return dy * (y > 0).to(dy.dtype)
+    if act == ACT_LRELU:
+        return torch.where(y > 0, dy, dy * 0.2)
+    if act == ACT_TANH:
+        return dy * (1 - y.float() * y.float()).to(dy.dtype)
+    raise ValueError(act)
+
+
+def _wgrad(x_buf, cin, dy_buf, cout, kh, kw, pad):
+    """dW (cout,cin,kh,kw) fp32 = sum over pixels of dY[p,co] * X[p+tap-pad,ci].  Staged implementation: cuDNN's
+    weight-gradient on channels-last views (library call; replaced by hrv_conv2d_wgrad in the kernel roadmap)."""
+    x = x_buf[..., :cin].permute(0, 3, 1, 2)
+    dy = dy_buf[..., :cout].permute(0, 3, 1, 2)
+    return torch.nn.grad.conv2d_weight(x, (cout, cin, kh, kw), dy, stride=1, padding=pad).float()
+
+
+class ConvFn(torch.autograd.Function):
+    """y = act(conv(x_buf[..., :cin], w, padding=pad) + bias (+ res_buf)) on (N,H,W,P) bf16 buffers, stride 1.
+    Output extent = H + 2*pad - kh + 1 ('same' for 3x3/1, 1x1/0; H+1 for the PatchGAN 4x4/2 and 2x2/1 forms).
+    need_wgrad=False skips dW (frozen nets: VGG, D inside the G step)."""
+
+    @staticmethod
+    def forward(ctx, x_buf, w, bias, res_buf, act, out_fp32_nchw, pad, out_f32_nhwc):
+        cout, cin, kh, kw = w.shape
+        n, h, wd, _ = x_buf.shape
+        oh, ow = h + 2 * pad - kh + 1, wd + 2 * pad - kw + 1
+        xa = Act(x_buf, c=cin)
+        pw = ops.pack_weight(w.detach(), (pad, pad))
+        b = bias.detach().float().contiguous() if bias is not None else None
+        res = Act(res_buf, c=cout) if res_buf is not None else None
+        if out_fp32_nchw:
+            y = torch.empty((n, cout, oh, ow), dtype=torch.float32, device=x_buf.device)
+            ops.conv2d(xa, pw, y, act=act, shift=b, res=res, out_layout=ops.capi.NCHW)
+        elif out_f32_nhwc:
+            ya = Act.empty(n, oh, ow, cout, dtype=torch.float32, pitch=cout)
+            ops.conv2d(xa, pw, ya, act=act, shift=b, res=res)
+            y = ya.buf
+        else:
+            ya = Act.empty(n, oh, ow, cout)
+            ops.conv2d(xa, pw, ya, act=act, shift=b, res=res)
+            y = ya.buf
+        ctx.save_for_backward(x_buf, w, y if act != ACT_NONE else None)
+        ctx.meta = (act, out_fp32_nchw, bias is not None, res_buf is not None, pad, out_f32_nhwc)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x_buf, w, y = ctx.saved_tensors
+        act, nchw, has_bias, has_res, pad, f32_nhwc = ctx.meta
+        cout, cin, kh, kw = w.shape
+        if nchw:  # fp32 NCHW upstream gradient (image output): bring it to the pixel-major bf16 convention
+            dv_buf = ops.from_nchw(_act_grad(dy, y, act).float().contiguous()).buf
+        elif f32_nhwc:
+            dv = _act_grad(dy, y, act)
+            dv_buf = torch.zeros(dv.shape[:3] + (ops.round_up(cout, 8),), dtype=torch.bfloat16, device=dv.device)
+            dv_buf[..., :cout] = dv.to(torch.bfloat16)
+        else:
+            dv_buf = _act_grad(dy, y, act).contiguous()
+        n, h, wd, _ = x_buf.shape
+        dx = dw = db = dres = None
+        if ctx.needs_input_grad[0]:
+            wt = w.detach().flip(2, 3).transpose(0, 1).contiguous()  # (cin, cout, kh, kw)
+            pw = ops.pack_weight(wt, (kh - 1 - pad, kw - 1 - pad))
+            dxa = Act.empty(n, h, wd, cin, pitch=x_buf.shape[3], zero=x_buf.shape[3] > ops.round_up(cin, 8))
+            ops.conv2d(Act(dv_buf, c=cout), pw, dxa)
+            dx = dxa.buf
+        if ctx.needs_input_grad[1]:
+            dw = _wgrad(x_buf, cin, dv_buf, cout, kh, kw, pad)
+        if has_bias and ctx.needs_input_grad[2]:
+            db = dv_buf[..., :cout].float().sum((0, 1, 2))
+        if has_res and ctx.needs_input_grad[3]:
+            dres = dv_buf
+        return dx, dw, db, dres, None, None, None, None
+
+
+def conv(x_buf, w, bias=None, res_buf=None, act=ACT_NONE, out_fp32_nchw=False, pad=None, out_f32_nhwc=False):
+    pad = w.shape[2] // 2 if pad is None else pad
+    return ConvFn.apply(x_buf, w, bias, res_buf, act, out_fp32_nchw, pad, out_f32_nhwc)
+
+
+class SpadeFn(torch.autograd.Function):
+    """h = act(InstanceNorm(xs + noise*ns) * (1 + conv(actv,Wg)+bg) + conv(actv,Wb)+bb), xs = cat(up2^shift(x0), x1)."""
+
+    @staticmethod
+    def forward(ctx, actv_buf, wg, wb, bg, bb, x0_buf, x1_buf, noise, ns, x0_shift, act):
+        n, h, w, _ = actv_buf.shape
+        c0 = x0_buf.shape[3]
+        c1 = x1_buf.shape[3] if x1_buf is not None else 0
+        C = c0 + c1
+        x0, x1 = Act(x0_buf), (Act(x1_buf) if x1_buf is not None else None)
+        nsd = ns.detach().float().contiguous()
+        mean, rstd = ops.instnorm_stats(x0, x0_shift, x1, h, w, noise, nsd)
+        gb = ops.pack_weight(wg.detach(), (1, 1), interleave=wb.detach())
+        gb_bias = torch.stack([bg.detach(), bb.detach()], 1).reshape(-1).float().contiguous()
+        out = Act.empty(n, h, w, C)
+        ops.conv2d_spade(Act(actv_buf, c=wg.shape[1]), gb, out, x0, x0_shift, x1, mean, rstd, noise, nsd, gb_bias, act)
+        ctx.save_for_backward(actv_buf, wg, wb, bg, bb, x0_buf, x1_buf, noise, ns, mean, rstd, out.buf)
+        ctx.meta = (x0_shift, act)
+        return out.buf
+
+    @staticmethod
+    def backward(ctx, dout):
+        actv_buf, wg, wb, bg, bb, x0_buf, x1_buf, noise, ns, mean, rstd, out = ctx.saved_tensors
+        x0_shift, act = ctx.meta
+        n, h, w, _ = actv_buf.shape
+        c0 = x0_buf.shape[3]
+        C = c0 + (x1_buf.shape[3] if x1_buf is not None else 0)
+        # ---- recompute the normalised operand and gamma (never stored by the fused forward)
+        xs = x0_buf
+        if x0_shift:
+            xs = xs.repeat_interleave(2, 1).repeat_interleave(2, 2)
+        if x1_buf is not None:
+            xs = torch.cat([xs, x1_buf], 3)
+        xn = (xs.float() + noise[..., None] * ns.detach().float() - mean[:, None, None, :]) * rstd[:, None, None, :]
+        gbw = ops.pack_weight(wg.detach(), (1, 1), interleave=wb.detach())
+        gb_bias = torch.stack([bg.detach(), bb.detach()], 1).reshape(-1).float().contiguous()
+        gbuf = Act.empty(n, h, w, 2 * C)
+        ops.conv2d(Act(actv_buf, c=wg.shape[1]), gbw, gbuf, shift=gb_bias)
+        gamma = gbuf.buf[..., 0::2].float()
+        # ---- modulation backward
+        dv = _act_grad(dout, out, act).float()
+        dgamma = dv * xn
+        dxn = dv * (1 + gamma)
+        dgb = torch.stack([dgamma, dv], 4).reshape(n, h, w, 2 * C).to(torch.bfloat16).contiguous()  # (dgamma_c, dbeta_c) pairs
+        # ---- InstanceNorm backward (biased variance): dx = rstd * (dxn - mean(dxn) - xn * mean(dxn*xn))
+        m1 = dxn.mean((1, 2), keepdim=True)
+        m2 = (dxn * xn).mean((1, 2), keepdim=True)
+        dxs = (dxn - m1 - xn * m2) * rstd[:, None, None, :]
+        dns = (dxs * noise[..., None]).sum((0, 1, 2)) if ctx.needs_input_grad[8] else None
+        dx0 = dxs[..., :c0]
+        if x0_shift:
+            dx0 = dx0.reshape(n, h // 2, 2, w // 2, 2, c0).sum((2, 4))
+        dx0 = dx0.to(torch.bfloat16).contiguous() if ctx.needs_input_grad[5] else None
+        dx1 = dxs[..., c0:].to(torch.bfloat16).contiguous() if (x1_buf is not None and ctx.needs_input_grad[6]) else None
+        # ---- gamma|beta GEMM backward
+        dactv = None
+        if ctx.needs_input_grad[0]:
+            wcat = torch.stack([wg.detach(), wb.detach()], 1).reshape(2 * C, *wg.shape[1:])  # interleaved rows
+            wt = wcat.flip(2, 3).transpose(0, 1).contiguous()
+            pw = ops.pack_weight(wt, (1, 1))
+            da = Act.empty(n, h, w, wg.shape[1], pitch=actv_buf.shape[3], zero=actv_buf.shape[3] > wg.shape[1])
+            ops.conv2d(Act(dgb), pw, da)
+            dactv = da.buf
+        dwcat = _wgrad(actv_buf, wg.shape[1], dgb, 2 * C, 3, 3, 1)
+        dbcat = dgb.float().sum((0, 1, 2))
+        return (dactv, dwcat[0::2].contiguous(), dwcat[1::2].contiguous(), dbcat[0::2].contiguous(), dbcat[1::2].contiguous(),
+                dx0, dx1, None, dns, None, None)
+
+
+class FromNCHW(torch.autograd.Function):
+    """fp32 NCHW -> pixel-major bf16 (with nearest resize); backward only when the input needs a gradient."""
+
+    @staticmethod
+    def forward(ctx, x, size, c_pad):
+        ctx.shape = x.shape
+        ctx.size = size
+        return ops.from_nchw(x.float().contiguous(), c_pad=c_pad, size=size).buf
+
+    @staticmethod
+    def backward(ctx, dbuf):
+        n, c, h, w = ctx.shape
+        if ctx.size is not None and tuple(ctx.size) != (h, w):
+            raise NotImplementedError("gradient through the nearest-resized input pyramid is never needed (inputs are data)")
+        return dbuf[..., :c].permute(0, 3, 1, 2).float().contiguous(), None, None
+
+
+def _block_train(blk, x0_buf, x0_shift, x1_buf, seg_buf, noise_fn, out_act):
+    """SPADEResBlock forward with autograd nodes (network_generator.py:157-173)."""
+    from .spade import _conv_weight_train
+    n, h, w, _ = seg_buf.shape
+
+    def spade(norm, x0b, sh, x1b, act):
+        cs = norm.conv_shared[0]
+        actv = conv(seg_buf, cs.weight, cs.bias, act=ACT_RELU)
+        return SpadeFn.apply(actv, norm.conv_gamma.weight, norm.conv_beta.weight, norm.conv_gamma.bias, norm.conv_beta.bias,
+                             x0b, x1b, noise_fn(n, h, w), norm.noise_scale, sh, act)
+
+    if blk.learned_shortcut:
+        hs = spade(blk.norm_s, x0_buf, x0_shift, x1_buf, ACT_NONE)
+        x_s = conv(hs, _conv_weight_train(blk.conv_s, blk.training))
+    else:
+        x_s = x0_buf
+    h0 = spade(blk.norm_0, x0_buf, x0_shift, x1_buf, ACT_LRELU)
+    dx = conv(h0, _conv_weight_train(blk.conv_0, blk.training), blk.conv_0.bias)
+    h1 = spade(blk.norm_1, dx, 0, None, ACT_LRELU)
+    return conv(h1, _conv_weight_train(blk.conv_1, blk.training), blk.conv_1.bias, res_buf=x_s, act=out_act)
+
+
+def generator_forward_train(g, x, seg):
+    """SPADEGenerator.forward with a differentiable graph (network_generator.py:221-245)."""
+    dev = x.device
+    noise_fn = g.noise_source or (lambda b, hh, ww: torch.randn(b, hh, ww, device=dev))
+    sizes = [(g.sh * 2 ** i, g.sw * 2 ** i) for i in range(8)]
+    x = x.float()
+    seg = seg.float()
+    feats, segs = [], []
+    for i, sz in enumerate(sizes):
+        s = FromNCHW.apply(x, sz, 16)
+        c = getattr(g, "conv_%d" % i)
+        feats.append(conv(s, c.weight, c.bias))
+        segs.append(ops.from_nchw(seg.detach(), size=sz).buf)
+    h = _block_train(g.head_0, feats[0], 0, None, segs[0], noise_fn, ACT_NONE)
+    names = g._blocks[1:]
+    for j, name in enumerate(names):
+        last = j == len(names) - 1
+        h = _block_train(getattr(g, name), h, 1, feats[j + 1], segs[j + 1], noise_fn, ACT_LRELU if last else ACT_NONE)
+    return conv(h, g.conv_img.weight, g.conv_img.bias, act=ACT_TANH, out_fp32_nchw=True)
+
+
+# ------------------------------------------------------------------------------------------------ discriminator (training)
+
+def space_to_depth_t(x_buf):
+    """Differentiable space-to-depth by 2 with zero fill of odd edges, channel order (py*2+px)*C + c
+    (same convention as hrv_space_to_depth / ops.s2d_weight). torch reshapes: pure data movement."""
+    n, h, w, c = x_buf.shape
+    if (h | w) & 1:
+        x_buf = F.pad(x_buf, (0, 0, 0, w & 1, 0, h & 1))
+        n, h, w, c = x_buf.shape
+    return x_buf.reshape(n, h // 2, 2, w // 2, 2, c).permute(0, 1, 3, 2, 4, 5).reshape(n, h // 2, w // 2, 4 * c).contiguous()
+
+
+class InstNormActFn(torch.autograd.Function):
+    """y = act(InstanceNorm(x)) on a pixel-major bf16 buffer (network_generator.py:427 + LeakyReLU)."""
+
+    @staticmethod
+    def forward(ctx, x_buf, act):
+        a = Act(x_buf)
+        mean, rstd = ops.instnorm_stats(a, 0, None, a.h, a.w, None, None)
+        y = Act.empty(a.n, a.h, a.w, a.c)
+        ops.instnorm_apply(a, mean, rstd, act, out=y)
+        ctx.save_for_backward(x_buf, mean, rstd, y.buf)
+        ctx.act = act
+        return y.buf
+
+    @staticmethod
+    def backward(ctx, dy):
+        x_buf, mean, rstd, y = ctx.saved_tensors
+        dxn = _act_grad(dy, y, ctx.act).float()
+        xn = (x_buf.float() - mean[:, None, None, :]) * rstd[:, None, None, :]
+        m1 = dxn.mean((1, 2), keepdim=True)
+        m2 = (dxn * xn).mean((1, 2), keepdim=True)
+        return ((dxn - m1 - xn * m2) * rstd[:, None, None, :]).to(torch.bfloat16), None
+
+
+def _nlayer_train(d, x_buf, need_wgrad):
+    """One NLayerDiscriminator (network_generator.py:250-291) on a pixel-major input; returns the per-group outputs."""
+    from .spade import _conv_weight_train
+    outs = []
+    h = x_buf
+    for i in range(d.n_groups):
+        first = getattr(d, "model%d" % i)[0]
+        convm = first[0] if isinstance(first, torch.nn.Sequential) else first
+        has_in = isinstance(first, torch.nn.Sequential) and d._instance
+        w = _conv_weight_train(convm, d.training)
+        if not need_wgrad:
+            w = w.detach()
+        bias = getattr(convm, "bias", None)
+        if bias is not None and not need_wgrad:
+            bias = bias.detach()
+        last = i == d.n_groups - 1
+        if convm.stride[0] == 2:
+            w2 = ops.s2d_weight(w, 2) if not w.requires_grad else _s2d_weight_t(w)
+            src = space_to_depth_t(h)
+            # k4 s2 p2 on (H,W) == k2 s1 p1 on the space-to-depth tensor; extent floor(H/2)+1
+            y = conv(src, w2, bias, act=ACT_NONE if has_in else ACT_LRELU, pad=1)
+            oh, ow = h.shape[1] // 2 + 1, h.shape[2] // 2 + 1
+            if y.shape[1] != oh or y.shape[2] != ow:
+                y = y[:, :oh, :ow].contiguous()
+        else:
+            y = conv(h, w, bias, pad=2, out_f32_nhwc=last)
+        if has_in:
+            y = InstNormActFn.apply(y, ACT_LRELU)
+        outs.append(y)
+        h = y
+    return outs
+
+
+def _s2d_weight_t(w):
+    """Differentiable version of ops.s2d_weight for k=4, pad=2 (index shuffle only)."""
+    cout, cin, k, _ = w.shape
+    assert k == 4
+    cin8 = ops.round_up(cin, 8)
+    wp = F.pad(w, (0, 0, 0, 0, 0, cin8 - cin))                      # (cout, cin8, 4, 4)
+    wp = wp.reshape(cout, cin8, 2, 2, 2, 2)                          # ky = ty*2+py, kx = tx*2+px
+    return wp.permute(0, 3, 5, 1, 2, 4).reshape(cout, 4 * cin8, 2, 2)  # channel = (py*2+px)*cin8 + ci, taps (ty,tx)
+
+
+def discriminator_forward_train(D, input_nchw, need_wgrad=True):
+    """MultiscaleDiscriminator.forward with autograd (network_generator.py:293-316); returns NCHW fp32 feature lists."""
+    x = FromNCHW.apply(input_nchw, None, None)
+    cin = input_nchw.shape[1]
+    result = []
+    ds = list(D.children())
+    cur = x
+    for k, d in enumerate(ds):
+        outs = _nlayer_train(d, cur, need_wgrad)
+        feats = []
+        for o in outs:
+            c = o.shape[3] if o.dtype != torch.float32 else 1
+            feats.append(o[..., :c].permute(0, 3, 1, 2).float())
+        result.append(feats if not D.no_ganFeat_loss else [feats[-1]])
+        if k + 1 < len(ds):
+            v = cur[..., :cin].permute(0, 3, 1, 2).float().contiguous()
+            v = F.avg_pool2d(v, 3, stride=2, padding=1, count_include_pad=False)
+            cur = FromNCHW.apply(v, None, None)
+    return result
+
+
+# ------------------------------------------------------------------------------------------------ VGG19 feature loss
+
+def vgg_features(vgg, x_nchw):
+    """Vgg19.forward (networks.py:201-231) through the conv kernels: conv3x3+bias+ReLU fused, 2x2 max-pool as a torch
+    data-movement op on the channels-last buffer.  Weights are frozen, so the backward is dgrad only (all ours).
+    Returns the 5 slice outputs as pixel-major bf16 buffers."""
+    h = FromNCHW.apply(x_nchw, None, None)
+    outs = []
+    for k in range(5):
+        for layer in getattr(vgg, "slice%d" % (k + 1)):
+            if isinstance(layer, torch.nn.Conv2d):
+                h = conv(h, layer.weight, layer.bias, act=ACT_RELU)
+            elif isinstance(layer, torch.nn.MaxPool2d):
+                h = F.max_pool2d(h.permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1).contiguous()
+            elif isinstance(layer, torch.nn.ReLU):
+                pass  # fused into the preceding convolution's epilogue
+            else:
+                raise NotImplementedError(type(layer).__name__)
+        outs.append(h)
+    return outs
+
+
+def vgg_loss(vgg, weights, x, y):
+    """VGGLoss.forward (networks.py:244-251): sum_i w_i * L1(vgg_i(x), vgg_i(y).detach())."""
+    n = x.shape[0]
+    f = vgg_features(vgg, torch.cat([x, y.detach()], 0))  # one pass over both images
+    loss = 0
+    for wgt, t in zip(weights, f):
+        loss = loss + wgt * (t[:n].float() - t[n:].float().detach()).abs().mean()
+    return loss

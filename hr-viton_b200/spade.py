@@ -96,6 +96,22 @@ def _conv_weight(conv, training):
     return conv.weight.detach()
 
 
+def _conv_weight_train(conv, training):
+    """Differentiable effective weight: W_orig / sigma with sigma = u.(W v) carrying the gradient through W (u, v are
+    buffers refreshed in place by one power iteration in training mode) — torch spectral_norm semantics."""
+    if hasattr(conv, "weight_orig"):
+        w = conv.weight_orig
+        wm = w.reshape(w.shape[0], -1)
+        u, v = conv.weight_u, conv.weight_v
+        if training:
+            with torch.no_grad():
+                v.copy_(torch.nn.functional.normalize(torch.mv(wm.t(), u), dim=0, eps=1e-12))
+                u.copy_(torch.nn.functional.normalize(torch.mv(wm, v), dim=0, eps=1e-12))
+        sigma = torch.dot(u.detach().clone(), torch.mv(wm, v.detach().clone()))
+        return w / sigma
+    return conv.weight
+
+
 class SPADENorm(nn.Module):
     """Parameter container of one SPADE normalisation (network_generator.py:75-99).  Its arithmetic runs inside
     SPADEResBlock.forward: hrv_instnorm_stats + the SPADE epilogue of hrv_conv2d_fwd."""

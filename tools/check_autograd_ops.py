@@ -1,0 +1,49 @@
+"""Per-op gradient check of hrviton_b200.autograd_g nodes against torch autograd (fp32, same GPU)."""
+import os, sys, torch
+import torch.nn.functional as F
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import hrv_loader; hrv_loader.load()
+from hrviton_b200 import autograd_g as ag, ops
+torch.manual_seed(0)
+dev = "cuda"
+
+def rel(a, b): return float((a.float() - b.float()).norm() / (b.float().norm() + 1e-12))
+
+def check_conv(cin, cout, k, pad, h, w, f32_nhwc=False, act=0):
+    x = torch.randn(2, cin, h, w, device=dev).bfloat16().float().requires_grad_(True)
+    wt = (torch.randn(cout, cin, k, k, device=dev) * 0.1).bfloat16().float().requires_grad_(True)
+    b = torch.randn(cout, device=dev).requires_grad_(True)
+    y_ref = F.conv2d(x, wt, b, padding=pad)
+    if act == 2: y_ref = F.leaky_relu(y_ref, 0.2)
+    R = torch.randn_like(y_ref)
+    (y_ref * R).sum().backward()
+    gx, gw, gb = x.grad.clone(), wt.grad.clone(), b.grad.clone()
+    x2 = x.detach().clone().requires_grad_(True); w2 = wt.detach().clone().requires_grad_(True); b2 = b.detach().clone().requires_grad_(True)
+    xb = ag.FromNCHW.apply(x2, None, None)
+    y = ag.conv(xb, w2, b2, act=act, pad=pad, out_f32_nhwc=f32_nhwc)
+    yn = y[..., :cout].permute(0, 3, 1, 2).float()
+    (yn * R).sum().backward()
+    print("conv %d->%d k%d p%d %dx%d f32=%s act=%d: fwd %.2e dx %.2e dw %.2e db %.2e" % (cin, cout, k, pad, h, w, f32_nhwc, act, rel(yn, y_ref), rel(x2.grad, gx), rel(w2.grad, gw), rel(b2.grad, gb)))
+
+check_conv(16, 32, 3, 1, 24, 16)
+check_conv(64, 64, 2, 1, 17, 13, act=2)
+check_conv(64, 1, 4, 2, 17, 13, f32_nhwc=True)
+check_conv(10, 16, 3, 1, 16, 12)
+# instnorm + lrelu
+x = torch.randn(2, 32, 17, 13, device=dev).bfloat16().float().requires_grad_(True)
+y_ref = F.leaky_relu(F.instance_norm(x), 0.2); R = torch.randn_like(y_ref); (y_ref * R).sum().backward()
+x2 = x.detach().clone().requires_grad_(True)
+y = ag.InstNormActFn.apply(ag.FromNCHW.apply(x2, None, None), 2)
+yn = y.permute(0, 3, 1, 2).float(); (yn * R).sum().backward()
+print("instnorm+lrelu: fwd %.2e dx %.2e" % (rel(yn, y_ref), rel(x2.grad, x.grad)))
+# s2d conv k4 s2 p2
+for (h, w) in [(16, 12), (17, 13)]:
+    x = torch.randn(2, 10, h, w, device=dev).bfloat16().float().requires_grad_(True)
+    wt = (torch.randn(24, 10, 4, 4, device=dev) * 0.1).bfloat16().float().requires_grad_(True)
+    y_ref = F.conv2d(x, wt, None, stride=2, padding=2); R = torch.randn_like(y_ref); (y_ref * R).sum().backward()
+    x2 = x.detach().clone().requires_grad_(True); w2 = wt.detach().clone().requires_grad_(True)
+    src = ag.space_to_depth_t(ag.FromNCHW.apply(x2, None, None))
+    y = ag.conv(src, ag._s2d_weight_t(w2), None, pad=1)
+    y = y[:, :y_ref.shape[2], :y_ref.shape[3], :24].permute(0, 3, 1, 2).float()
+    (y * R).sum().backward()
+    print("s2d conv %dx%d: fwd %.2e dx %.2e dw %.2e" % (h, w, rel(y, y_ref), rel(x2.grad, x.grad), rel(w2.grad, wt.grad)))
