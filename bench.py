@@ -6,7 +6,10 @@
     python bench.py --impl reference ...      # the reference algorithm on the host CPU cores (oracle port)
 
 Prints ONE JSON line on rank 0.  Workloads (config.workload):
-  gen_fwd    SPADEGenerator inference forward, 1024x768, per-GPU batch 8, bf16 activations (BASELINE.json configs[2])
+  train_stage2  (default) one full train_generator.py step per "step": frozen tocg -> warp -> SPADE G fwd+bwd -> D fwd+bwd
+                (hinge + feature matching) + VGG loss -> Adam(G), then the D update (2nd G fwd, D fwd+bwd, Adam(D)),
+                1024x768, bf16 activations (BASELINE.json configs[3], per-GPU batch --batch)
+  gen_fwd       SPADEGenerator inference forward, 1024x768, per-GPU batch 8 (BASELINE.json configs[2])
 """
 import argparse
 import json
@@ -152,15 +155,52 @@ def cpu_baseline_gen(steps=1, warmup=0, budget_s=240.0):
             "s_per_image": med, "steps_done": len(times)}
 
 
+def cpu_baseline_train(budget_s=240.0):
+    """Bounded CPU sample of the training workload: the oracle port's SPADEGenerator forward + backward (the 56 % of the
+    stage-2 step's FLOPs that dominate it) on ONE 512x384 image, fp32, host cores; reported as
+    1024x768-equivalent images/s (x 1/4: the generator is fully convolutional, cost scales with pixels)."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import hrviton_oracle as orc
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(min(cores, 64))
+    import network_generator
+    torch.manual_seed(0)
+    opt = gen_opt()
+    opt.fine_height, opt.fine_width = 512, 384
+    m = network_generator.SPADEGenerator(opt, 9)
+    m.init_weights("xavier", 0.02)
+    sd = {k: v.detach().clone().requires_grad_(v.is_floating_point() and not k.endswith(("weight_u", "weight_v"))) for k, v in m.state_dict().items()}
+    x = torch.rand(1, 9, 512, 384) * 2 - 1
+    seg = torch.zeros(1, 7, 512, 384)
+    seg[:, 0] = 1
+    t0 = time.time()
+    out = orc.spade_generator_forward(sd, x, seg, lambda b, hh, ww: torch.randn(b, hh, ww))
+    out.mean().backward()
+    dt = time.time() - t0
+    return {"value": 0.25 / dt, "unit": "images/s", "cores": min(cores, 64), "kind": "port",
+            "sample": "oracle SPADEGenerator fwd+bwd fp32 on one 512x384 image (%.1f s), scaled x1/4 to 1024x768; G fwd+bwd is ~56%% of the stage-2 step FLOPs, so the full-step CPU rate is lower still" % dt,
+            "s_per_sample": dt}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cb = cpu_baseline_gen(steps=max(1, args.steps), warmup=min(args.warmup, 1))
+    if args.workload == "train_stage2":
+        vals = [cpu_baseline_train() for _ in range(max(1, min(args.steps, 3)))]
+        vals.sort(key=lambda c: c["value"])
+        cb = vals[len(vals) // 2]
+        cb["steps_done"] = len(vals)
+        cb["s_per_image"] = cb["s_per_sample"] * 4
+        wl = "train_stage2 (bounded sample: generator fwd+bwd only, 512x384, pixel-scaled; reference algorithm on host CPU)"
+    else:
+        cb = cpu_baseline_gen(steps=max(1, args.steps), warmup=min(args.warmup, 1))
+        wl = "gen_fwd: SPADEGenerator inference forward 1024x768 (reference algorithm, host CPU, 1 image per step)"
     line = {"impl": "reference", "metric": "1024x768 try-on images/sec", "value": cb["value"], "unit": "images/s", "n_gpus": args.gpus,
             "steps": cb["steps_done"], "warmup": min(args.warmup, 1), "ms_per_step": cb["s_per_image"] * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "gen_fwd: SPADEGenerator inference forward 1024x768 (reference algorithm, host CPU, 1 image per step)"},
+            "config": {"workload": wl},
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -172,8 +212,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=8, help="per-GPU batch")
-    ap.add_argument("--workload", default="gen_fwd", choices=["gen_fwd"])
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: 4 for train_stage2, 8 for gen_fwd)")
+    ap.add_argument("--workload", default="train_stage2", choices=["train_stage2", "gen_fwd"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dump-profile", default="", help="write the per-launch CUDA-event profile of one step as CSV")
     args = ap.parse_args()
@@ -195,29 +235,72 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     W_ = max(3, args.warmup)
-    K, B = args.steps, args.batch
-
-    g = build_generator(dev)
-    x_h, seg_h = synth_batch(B, "cpu", 100 + rank)
-    x_h, seg_h = x_h.pin_memory(), seg_h.pin_memory()
-    x_d, seg_d = x_h.to(dev), seg_h.to(dev)
-    out_h = torch.empty((B, 3, H, W), dtype=torch.float32).pin_memory()
+    K = args.steps
+    train = args.workload == "train_stage2"
+    B = args.batch or (4 if train else 8)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_resident():
+    if train:
+        os.environ.setdefault("HRV_VGG_RANDOM_INIT", "1")  # no network: torchvision weights cannot be downloaded
+        import network_generator
+        import networks
+        from hrviton_b200 import ddp, train_step
+        topt = types.SimpleNamespace(warp_feature="T1", out_layer="relu", cuda=True)
+        torch.manual_seed(0)
+        tocg = networks.ConditionGenerator(topt, 4, 16, 13, ngf=96, norm_layer=torch.nn.BatchNorm2d)
         with torch.no_grad():
-            return g(x_d, seg_d)
+            for mod in tocg.modules():
+                if isinstance(mod, torch.nn.BatchNorm2d):
+                    mod.running_mean.normal_(0, 0.1)
+                    mod.running_var.uniform_(0.5, 1.5)
+        tocg = tocg.to(dev).eval()
+        g = build_generator(dev).train()
+        dopt = gen_opt()
+        dopt.ndf, dopt.norm_D, dopt.n_layers_D, dopt.num_D, dopt.no_ganFeat_loss = 64, "spectralinstance", 3, 2, False
+        D = network_generator.MultiscaleDiscriminator(dopt)
+        D.init_weights("xavier", 0.02)
+        D = D.to(dev).train()
+        vgg = networks.Vgg19().to(dev).eval()
+        reducers = {}
+        if world > 1:
+            reducers = {"G": ddp.GradBucketReducer(list(g.parameters())), "D": ddp.GradBucketReducer(list(D.parameters()))}
+        trainer = train_step.Stage2Trainer(tocg, g, D, vgg, reducers=reducers)
+        batch_h = {k: v.pin_memory() for k, v in train_step.synthetic_batch(B, H, W, "cpu", seed=100 + rank).items()}
+        batch_d = {k: v.to(dev) for k, v in batch_h.items()}
+        loss_h = torch.empty(2, dtype=torch.float32).pin_memory()
+        h2d_bytes = int(sum(v.numel() * v.element_size() for v in batch_h.values()))
+        d2h_bytes = 8
 
-    def step_e2e():
-        with torch.no_grad():
-            xd = x_h.to(dev, non_blocking=True)
-            sd = seg_h.to(dev, non_blocking=True)
-            out = g(xd, sd)
-            out_h.copy_(out, non_blocking=True)
+        def step_resident():
+            return trainer.step(batch_d, H, W)
+
+        def step_e2e():
+            bd = {k: v.to(dev, non_blocking=True) for k, v in batch_h.items()}
+            out = trainer.step(bd, H, W)
+            loss_h.copy_(torch.stack([out["loss_gen"].float(), out["loss_dis"].float()]), non_blocking=True)
+    else:
+        g = build_generator(dev)
+        x_h, seg_h = synth_batch(B, "cpu", 100 + rank)
+        x_h, seg_h = x_h.pin_memory(), seg_h.pin_memory()
+        x_d, seg_d = x_h.to(dev), seg_h.to(dev)
+        out_h = torch.empty((B, 3, H, W), dtype=torch.float32).pin_memory()
+        h2d_bytes = int(x_h.numel() * 4 + seg_h.numel() * 4)
+        d2h_bytes = int(out_h.numel() * 4)
+
+        def step_resident():
+            with torch.no_grad():
+                return g(x_d, seg_d)
+
+        def step_e2e():
+            with torch.no_grad():
+                xd = x_h.to(dev, non_blocking=True)
+                sd = seg_h.to(dev, non_blocking=True)
+                out = g(xd, sd)
+                out_h.copy_(out, non_blocking=True)
 
     def timed(fn, k):
         barrier()
@@ -287,21 +370,22 @@ def main():
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu_baseline = cpu_baseline_gen(steps=1, warmup=0)
+        cpu_baseline = cpu_baseline_train() if train else cpu_baseline_gen(steps=1, warmup=0)
         cpu_baseline = {k: cpu_baseline[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     if rank == 0:
         line = {"metric": "1024x768 try-on images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W_,
                 "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
                 "data": "synthetic",
-                "config": {"workload": "gen_fwd: SPADEGenerator inference forward (fwd only — backward not built yet), 1024x768, bf16 activations, fp32 accumulate",
+                "config": {"workload": ("train_stage2: full train_generator.py step (tocg fwd, G fwd+bwd, D fwd+bwd x2, 2nd G fwd, VGG loss fwd+dgrad, Adam x2), 1024x768, bf16 activations / fp32 accumulate; conv wgrad still via cuDNN (staged), everything else on this repo's kernels or torch glue"
+                                        if train else "gen_fwd: SPADEGenerator inference forward, 1024x768, bf16 activations, fp32 accumulate"),
                            "per_gpu_batch": B, "global_batch": B * world, "parallelism": "dp%d" % world,
                            "l2": "activations per step (>10 GB) exceed the 126 MB L2; no explicit flush",
                            "weights": "xavier(0.02) random init, noise_scale~N(0,0.1)"},
                 "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": ms_e2e / K,
-                        "h2d_bytes_per_step": int(x_h.numel() * 4 + seg_h.numel() * 4), "d2h_bytes_per_step": int(out_h.numel() * 4)},
+                        "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernel_breakdown": breakdown,
-                "model_tflops": GEN_GFLOP_PER_IMG * value / 1e3}
+                "model_tflops": (8800.0 if train else GEN_GFLOP_PER_IMG) * value / 1e3}
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
         print(json.dumps(line))

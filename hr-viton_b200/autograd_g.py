@@ -108,7 +108,10 @@ def conv(x_buf, w, bias=None, res_buf=None, act=ACT_NONE, out_fp32_nchw=False, p
 
 
 class SpadeFn(torch.autograd.Function):
-    """h = act(InstanceNorm(xs + noise*ns) * (1 + conv(actv,Wg)+bg) + conv(actv,Wb)+bb), xs = cat(up2^shift(x0), x1)."""
+    """h = act(InstanceNorm(xs + noise*ns) * (1 + conv(actv,Wg)+bg) + conv(actv,Wb)+bb), xs = cat(up2^shift(x0), x1).
+    Forward: hrv_instnorm_stats + hrv_conv2d_fwd (SPADE epilogue, which also emits gamma for the backward).
+    Backward: hrv_norm_bwd_reduce / hrv_norm_bwd_apply (fused modulation + InstanceNorm backward), then the dgrad of the
+    gamma|beta GEMM through hrv_conv2d_fwd and its weight gradient."""
 
     @staticmethod
     def forward(ctx, actv_buf, wg, wb, bg, bb, x0_buf, x1_buf, noise, ns, x0_shift, act):
@@ -122,58 +125,32 @@ class SpadeFn(torch.autograd.Function):
         gb = ops.pack_weight(wg.detach(), (1, 1), interleave=wb.detach())
         gb_bias = torch.stack([bg.detach(), bb.detach()], 1).reshape(-1).float().contiguous()
         out = Act.empty(n, h, w, C)
-        ops.conv2d_spade(Act(actv_buf, c=wg.shape[1]), gb, out, x0, x0_shift, x1, mean, rstd, noise, nsd, gb_bias, act)
-        ctx.save_for_backward(actv_buf, wg, wb, bg, bb, x0_buf, x1_buf, noise, ns, mean, rstd, out.buf)
+        gamma = Act.empty(n, h, w, C)
+        ops.conv2d_spade(Act(actv_buf, c=wg.shape[1]), gb, out, x0, x0_shift, x1, mean, rstd, noise, nsd, gb_bias, act, gamma_out=gamma)
+        ctx.save_for_backward(actv_buf, wg, wb, x0_buf, x1_buf, noise, nsd, mean, rstd, out.buf, gamma.buf)
         ctx.meta = (x0_shift, act)
         return out.buf
 
     @staticmethod
     def backward(ctx, dout):
-        actv_buf, wg, wb, bg, bb, x0_buf, x1_buf, noise, ns, mean, rstd, out = ctx.saved_tensors
+        actv_buf, wg, wb, x0_buf, x1_buf, noise, nsd, mean, rstd, out, gamma = ctx.saved_tensors
         x0_shift, act = ctx.meta
         n, h, w, _ = actv_buf.shape
-        c0 = x0_buf.shape[3]
-        C = c0 + (x1_buf.shape[3] if x1_buf is not None else 0)
-        # ---- recompute the normalised operand and gamma (never stored by the fused forward)
-        xs = x0_buf
-        if x0_shift:
-            xs = xs.repeat_interleave(2, 1).repeat_interleave(2, 2)
-        if x1_buf is not None:
-            xs = torch.cat([xs, x1_buf], 3)
-        xn = (xs.float() + noise[..., None] * ns.detach().float() - mean[:, None, None, :]) * rstd[:, None, None, :]
-        gbw = ops.pack_weight(wg.detach(), (1, 1), interleave=wb.detach())
-        gb_bias = torch.stack([bg.detach(), bb.detach()], 1).reshape(-1).float().contiguous()
-        gbuf = Act.empty(n, h, w, 2 * C)
-        ops.conv2d(Act(actv_buf, c=wg.shape[1]), gbw, gbuf, shift=gb_bias)
-        gamma = gbuf.buf[..., 0::2].float()
-        # ---- modulation backward
-        dv = _act_grad(dout, out, act).float()
-        dgamma = dv * xn
-        dxn = dv * (1 + gamma)
-        dgb = torch.stack([dgamma, dv], 4).reshape(n, h, w, 2 * C).to(torch.bfloat16).contiguous()  # (dgamma_c, dbeta_c) pairs
-        # ---- InstanceNorm backward (biased variance): dx = rstd * (dxn - mean(dxn) - xn * mean(dxn*xn))
-        m1 = dxn.mean((1, 2), keepdim=True)
-        m2 = (dxn * xn).mean((1, 2), keepdim=True)
-        dxs = (dxn - m1 - xn * m2) * rstd[:, None, None, :]
-        dns = (dxs * noise[..., None]).sum((0, 1, 2)) if ctx.needs_input_grad[8] else None
-        dx0 = dxs[..., :c0]
-        if x0_shift:
-            dx0 = dx0.reshape(n, h // 2, 2, w // 2, 2, c0).sum((2, 4))
-        dx0 = dx0.to(torch.bfloat16).contiguous() if ctx.needs_input_grad[5] else None
-        dx1 = dxs[..., c0:].to(torch.bfloat16).contiguous() if (x1_buf is not None and ctx.needs_input_grad[6]) else None
-        # ---- gamma|beta GEMM backward
+        C = x0_buf.shape[3] + (x1_buf.shape[3] if x1_buf is not None else 0)
+        dgb, dx0, dx1, dns, sum_dg, sum_db = ops.norm_bwd(
+            Act(dout.contiguous()), Act(out), Act(gamma), Act(x0_buf), x0_shift, Act(x1_buf) if x1_buf is not None else None,
+            noise, nsd, mean, rstd, act, want_dgb=True)
         dactv = None
         if ctx.needs_input_grad[0]:
-            wcat = torch.stack([wg.detach(), wb.detach()], 1).reshape(2 * C, *wg.shape[1:])  # interleaved rows
-            wt = wcat.flip(2, 3).transpose(0, 1).contiguous()
-            pw = ops.pack_weight(wt, (1, 1))
+            wcat = torch.stack([wg.detach(), wb.detach()], 1).reshape(2 * C, *wg.shape[1:])  # interleaved (gamma_c, beta_c) rows
+            pw = ops.pack_weight(wcat.flip(2, 3).transpose(0, 1).contiguous(), (1, 1))
             da = Act.empty(n, h, w, wg.shape[1], pitch=actv_buf.shape[3], zero=actv_buf.shape[3] > wg.shape[1])
-            ops.conv2d(Act(dgb), pw, da)
+            ops.conv2d(dgb, pw, da)
             dactv = da.buf
-        dwcat = _wgrad(actv_buf, wg.shape[1], dgb, 2 * C, 3, 3, 1)
-        dbcat = dgb.float().sum((0, 1, 2))
-        return (dactv, dwcat[0::2].contiguous(), dwcat[1::2].contiguous(), dbcat[0::2].contiguous(), dbcat[1::2].contiguous(),
-                dx0, dx1, None, dns, None, None)
+        dwcat = _wgrad(actv_buf, wg.shape[1], dgb.buf, 2 * C, 3, 3, 1)
+        return (dactv, dwcat[0::2].contiguous(), dwcat[1::2].contiguous(), sum_dg, sum_db,
+                dx0.buf if ctx.needs_input_grad[5] else None,
+                dx1.buf if (dx1 is not None and ctx.needs_input_grad[6]) else None, None, dns, None, None)
 
 
 class FromNCHW(torch.autograd.Function):
@@ -249,7 +226,8 @@ def space_to_depth_t(x_buf):
 
 
 class InstNormActFn(torch.autograd.Function):
-    """y = act(InstanceNorm(x)) on a pixel-major bf16 buffer (network_generator.py:427 + LeakyReLU)."""
+    """y = act(InstanceNorm(x)) on a pixel-major bf16 buffer (network_generator.py:427 + LeakyReLU); backward through the
+    same fused kernels as the SPADE norms (no modulation, no noise)."""
 
     @staticmethod
     def forward(ctx, x_buf, act):
@@ -264,11 +242,9 @@ class InstNormActFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         x_buf, mean, rstd, y = ctx.saved_tensors
-        dxn = _act_grad(dy, y, ctx.act).float()
-        xn = (x_buf.float() - mean[:, None, None, :]) * rstd[:, None, None, :]
-        m1 = dxn.mean((1, 2), keepdim=True)
-        m2 = (dxn * xn).mean((1, 2), keepdim=True)
-        return ((dxn - m1 - xn * m2) * rstd[:, None, None, :]).to(torch.bfloat16), None
+        _, dx, _, _, _, _ = ops.norm_bwd(Act(dy.contiguous()), Act(y), None, Act(x_buf), 0, None, None, None, mean, rstd, ctx.act,
+                                         want_dgb=False)
+        return dx.buf, None
 
 
 def _nlayer_train(d, x_buf, need_wgrad):

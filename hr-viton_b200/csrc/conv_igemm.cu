@@ -56,6 +56,8 @@ struct alignas(64) ConvArgs {
   const float* noise;
   const float* noise_scale;
   int C_mod;
+  __nv_bfloat16* gamma_out;
+  int gamma_pitch;
 };
 
 template <int BK>
@@ -424,14 +426,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
           if (!live) continue;
           const float xs[8] = {bf16_lo(xv.x), bf16_hi(xv.x), bf16_lo(xv.y), bf16_hi(xv.y),
                                bf16_lo(xv.z), bf16_hi(xv.z), bf16_lo(xv.w), bf16_hi(xv.w)};
-          float o[8];
+          float o[8], gmv[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float xval = fmaf(nz, nsv[i], xs[i]);
             const float gm = __uint_as_float(v[2 * i]) + sh[2 * i];
             const float bt = __uint_as_float(v[2 * i + 1]) + sh[2 * i + 1];
             const float xn = (xval - mu[i]) * rs[i];
+            gmv[i] = gm;
             o[i] = apply_act(fmaf(xn, 1.f + gm, bt), a.act);
+          }
+          if (a.gamma_out) {  // training: keep gamma for the backward pass (saves re-running this GEMM)
+            uint4 gv;
+            gv.x = pack_bf16(gmv[0], gmv[1]); gv.y = pack_bf16(gmv[2], gmv[3]);
+            gv.z = pack_bf16(gmv[4], gmv[5]); gv.w = pack_bf16(gmv[6], gmv[7]);
+            *reinterpret_cast<uint4*>(a.gamma_out + pix * a.gamma_pitch + c0) = gv;
           }
           uint4 ov;
           ov.x = pack_bf16(o[0], o[1]); ov.y = pack_bf16(o[2], o[3]);
@@ -554,6 +563,11 @@ extern "C" int hrv_conv2d_fwd(const hrv_conv_params* p, hrv_stream stream) {
     a.x0 = (const __nv_bfloat16*)p->x0.ptr; a.x0_c = p->x0.c; a.x0_pitch = p->x0.pitch; a.x0_shift = p->x0_shift ? 1 : 0;
     a.x1 = (const __nv_bfloat16*)p->x1.ptr; a.x1_pitch = p->x1.pitch;
     a.mean = p->mean; a.rstd = p->rstd; a.noise = p->noise; a.noise_scale = p->noise_scale; a.C_mod = C;
+    if (p->gamma_out.ptr) {
+      if (p->gamma_out.dtype != HRV_BF16 || ((uintptr_t)p->gamma_out.ptr & 15) || (p->gamma_out.pitch % 8) || p->gamma_out.c != C)
+        return set_error(HRV_EINVAL, "conv(spade): gamma_out must be bf16 (n,h,w,C), 16-byte aligned");
+      a.gamma_out = (__nv_bfloat16*)p->gamma_out.ptr; a.gamma_pitch = p->gamma_out.pitch;
+    }
   } else if (p->epi != HRV_EPI_LINEAR) {
     return set_error(HRV_EINVAL, "conv: unknown epilogue %d", p->epi);
   }

@@ -202,13 +202,14 @@ def conv2d(inp, pw, out, act=ACT_NONE, scale=None, shift=None, res=None, out_lay
     p.res = res.ct() if res is not None else _NULL
     p.x0 = _NULL
     p.x1 = _NULL
+    p.gamma_out = _NULL
     with _Timed("conv", pw.flops_per_pixel * p.out.n * p.out.h * p.out.w,
                 label="%d->%d k%dx%d n%d %dx%d bk%d bn%d" % (inp.c, pw.n_gemm, pw.kh, pw.kw, p.out.n, p.out.h, p.out.w, pw.bk, pw.bn)):
         capi.check(capi.lib().hrv_conv2d_fwd(ctypes.byref(p), _stream()), "conv2d_fwd")
     return out
 
 
-def conv2d_spade(actv, pw, out, x0, x0_shift, x1, mean, rstd, noise, noise_scale, shift, act):
+def conv2d_spade(actv, pw, out, x0, x0_shift, x1, mean, rstd, noise, noise_scale, shift, act, gamma_out=None):
     p = capi.ConvParams()
     p.inp = actv.ct()
     p.wpack = pw.w.data_ptr()
@@ -225,6 +226,7 @@ def conv2d_spade(actv, pw, out, x0, x0_shift, x1, mean, rstd, noise, noise_scale
     p.x1 = x1.ct() if x1 is not None else _NULL
     p.x0_shift = x0_shift
     p.mean, p.rstd, p.noise, p.noise_scale = _p(mean), _p(rstd), _p(noise), _p(noise_scale)
+    p.gamma_out = gamma_out.ct() if gamma_out is not None else _NULL
     with _Timed("conv_spade", pw.flops_per_pixel * out.n * out.h * out.w,
                 label="%d->%d k%dx%d n%d %dx%d bk%d bn%d" % (actv.c, pw.n_gemm, pw.kh, pw.kw, out.n, out.h, out.w, pw.bk, pw.bn)):
         capi.check(capi.lib().hrv_conv2d_fwd(ctypes.byref(p), _stream()), "conv2d_fwd(spade)")
@@ -317,3 +319,44 @@ def flow_warp(flow_lo, src, dst, want_flow_up=True, want_idx=False):
                                         ctypes.byref(ts), ctypes.byref(td), _p(flow_up), _p(idx), _stream()), "flow_warp")
     LAUNCHES[0] += 1
     return flow_up, idx
+
+
+def norm_bwd(dh, h, gamma, x0, x0_shift, x1, noise, noise_scale, mean, rstd, act, want_dgb):
+    """Fused backward of the SPADE modulation + InstanceNorm (gamma given) or of InstanceNorm + activation (gamma None).
+    Returns (dgb Act | None, dx0 Act, dx1 Act | None, d_noise_scale fp32 [C] | None, sum_dgamma fp32 [C], sum_dbeta fp32 [C])."""
+    n, H, W = dh.n, dh.h, dh.w
+    c0 = x0.c
+    c1 = x1.c if x1 is not None else 0
+    C = c0 + c1
+    dev = dh.buf.device
+    dxn = Act.empty(n, H, W, C)
+    dgb = Act.empty(n, H, W, 2 * C) if want_dgb else None
+    sums = torch.empty((n, C, 4), dtype=torch.float64, device=dev)
+    tdh, tx0, tdxn = dh.ct(), x0.ct(), dxn.ct()
+    th = h.ct() if h is not None else _NULL
+    tg = gamma.ct() if gamma is not None else _NULL
+    tx1 = x1.ct() if x1 is not None else _NULL
+    tdgb = dgb.ct() if dgb is not None else _NULL
+    with _Timed("norm_bwd", n * H * W * C * 2.0 * (4 + (1 if gamma is not None else 0) + (2 if want_dgb else 0)), launches=2):
+        capi.check(capi.lib().hrv_norm_bwd_reduce(ctypes.byref(tdh), ctypes.byref(th), ctypes.byref(tg), ctypes.byref(tx0), x0_shift,
+                                                  ctypes.byref(tx1), H, W, _p(noise), _p(noise_scale), mean.data_ptr(), rstd.data_ptr(),
+                                                  act, ctypes.byref(tdgb), ctypes.byref(tdxn), sums.data_ptr(), _stream()), "norm_bwd_reduce")
+    inv = 1.0 / float(H * W)
+    m1 = (sums[:, :, 0] * inv).float().contiguous()
+    m2 = (sums[:, :, 1] * inv).float().contiguous()
+    dns = torch.zeros(C, dtype=torch.float64, device=dev) if noise_scale is not None else None
+    dx0 = Act.empty(n, x0.h, x0.w, c0)
+    tdx0 = dx0.ct()
+    with _Timed("norm_bwd", n * H * W * c0 * 2.0 * 2, launches=1):
+        capi.check(capi.lib().hrv_norm_bwd_apply(ctypes.byref(tdxn), ctypes.byref(tx0), x0_shift, 0, C, H, W, _p(noise), _p(noise_scale),
+                                                 mean.data_ptr(), rstd.data_ptr(), m1.data_ptr(), m2.data_ptr(), ctypes.byref(tdx0),
+                                                 _p(dns), _stream()), "norm_bwd_apply(x0)")
+    dx1 = None
+    if x1 is not None:
+        dx1 = Act.empty(n, H, W, c1)
+        tdx1 = dx1.ct()
+        with _Timed("norm_bwd", n * H * W * c1 * 2.0 * 3, launches=1):
+            capi.check(capi.lib().hrv_norm_bwd_apply(ctypes.byref(tdxn), ctypes.byref(tx1), 0, c0, C, H, W, _p(noise), _p(noise_scale),
+                                                     mean.data_ptr(), rstd.data_ptr(), m1.data_ptr(), m2.data_ptr(), ctypes.byref(tdx1),
+                                                     _p(dns), _stream()), "norm_bwd_apply(x1)")
+    return dgb, dx0, dx1, (dns.float() if dns is not None else None), sums[:, :, 2].sum(0).float(), sums[:, :, 3].sum(0).float()

@@ -77,6 +77,7 @@ typedef struct hrv_conv_params {
   const float* rstd;  /* [N][C] */
   const float* noise; /* [N][H][W] or NULL */
   const float* noise_scale; /* [C] or NULL */
+  hrv_tensor gamma_out; /* SPADE only, optional (ptr NULL = none): bf16 (n,h,w,C) receives gamma (incl. bias) for the backward pass */
 } hrv_conv_params;
 
 int hrv_conv2d_fwd(const hrv_conv_params* p, hrv_stream stream);
@@ -94,6 +95,24 @@ int hrv_instnorm_stats(const hrv_tensor* x0, int32_t x0_shift, const hrv_tensor*
  * discriminators, network_generator.py:269-270,427; networks.py:366-386). In place allowed. */
 int hrv_instnorm_apply(const hrv_tensor* x, const float* mean, const float* rstd, int32_t act,
                        const hrv_tensor* y, hrv_stream stream);
+
+/* Backward of  h = act(xn*(1+gamma)+beta),  xn = InstanceNorm(cat(up2^x0_shift(x0), x1) + noise*noise_scale)
+ * (network_generator.py:101-122,170-171), pass 1 of 2: per element dv = dh*act'(h), dgamma = dv*xn, dbeta = dv,
+ * dxn = dv*(1+gamma); writes dgb (bf16 (n,h,w,2C), columns 2c = dgamma_c, 2c+1 = dbeta_c = dY of the gamma|beta GEMM; optional)
+ * and dxn (bf16 (n,h,w,C)); accumulates sums[N][C][4] (fp64, zeroed by the call) = {sum dxn, sum dxn*xn, sum dgamma, sum dbeta}.
+ * gamma == NULL means plain InstanceNorm + activation (the discriminators): dxn = dv. h is ignored when act == NONE. */
+int hrv_norm_bwd_reduce(const hrv_tensor* dh, const hrv_tensor* h, const hrv_tensor* gamma, const hrv_tensor* x0,
+                        int32_t x0_shift, const hrv_tensor* x1, int32_t H, int32_t W, const float* noise,
+                        const float* noise_scale, const float* mean, const float* rstd, int32_t act,
+                        const hrv_tensor* dgb, const hrv_tensor* dxn, double* sums, hrv_stream stream);
+
+/* Pass 2: InstanceNorm backward dxs = rstd*(dxn - m1 - xn*m2) (m1 = sum dxn / HW, m2 = sum dxn*xn / HW, [N][C] fp32) for the
+ * channel slice [c_off, c_off+src.c) of the virtual input; src = x0 (shift = x0_shift: the 2x2 children of every source pixel are
+ * summed = backward of the nearest up-sampling) or x1 (shift 0). Writes dx (bf16, src extent) and accumulates
+ * dns[c] += sum dxs*noise (fp64 [C], caller-zeroed; may be NULL). */
+int hrv_norm_bwd_apply(const hrv_tensor* dxn, const hrv_tensor* src, int32_t shift, int32_t c_off, int32_t C, int32_t H,
+                       int32_t W, const float* noise, const float* noise_scale, const float* mean, const float* rstd,
+                       const float* m1, const float* m2, const hrv_tensor* dx, double* dns, hrv_stream stream);
 
 /* fp32 NCHW -> bf16 NHWC with nearest resampling to (dst.h, dst.w): src index = floor(dst*in/out)
  * (F.interpolate(mode='nearest'), network_generator.py:164,222) and zero fill of dst channels >= C.
