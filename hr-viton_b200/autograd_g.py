@@ -77,16 +77,24 @@ class ConvFn(torch.autograd.Function):
         x_buf, w, y = ctx.saved_tensors
         act, nchw, has_bias, has_res, pad, f32_nhwc = ctx.meta
         cout, cin, kh, kw = w.shape
+        db = None
         if nchw:  # fp32 NCHW upstream gradient (image output): bring it to the pixel-major bf16 convention
-            dv_buf = ops.from_nchw(_act_grad(dy, y, act).float().contiguous()).buf
+            dv32 = _act_grad(dy, y, act).float()
+            if has_bias and ctx.needs_input_grad[2]:
+                db = dv32.sum((0, 2, 3))
+            dv_buf = ops.from_nchw(dv32.contiguous()).buf
         elif f32_nhwc:
             dv = _act_grad(dy, y, act)
+            if has_bias and ctx.needs_input_grad[2]:
+                db = dv.sum((0, 1, 2), dtype=torch.float32)
             dv_buf = torch.zeros(dv.shape[:3] + (ops.round_up(cout, 8),), dtype=torch.bfloat16, device=dv.device)
             dv_buf[..., :cout] = dv.to(torch.bfloat16)
-        else:
-            dv_buf = _act_grad(dy, y, act).contiguous()
+        else:  # one fused pass: activation backward + bias gradient
+            want_b = has_bias and ctx.needs_input_grad[2]
+            dva, db = ops.act_bwd_bias(Act(dy.contiguous(), c=cout), Act(y, c=cout) if y is not None else None, act, want_bias=want_b)
+            dv_buf = dva.buf
         n, h, wd, _ = x_buf.shape
-        dx = dw = db = dres = None
+        dx = dw = dres = None
         if ctx.needs_input_grad[0]:
             wt = w.detach().flip(2, 3).transpose(0, 1).contiguous()  # (cin, cout, kh, kw)
             pw = ops.pack_weight(wt, (kh - 1 - pad, kw - 1 - pad))
@@ -95,8 +103,6 @@ class ConvFn(torch.autograd.Function):
             dx = dxa.buf
         if ctx.needs_input_grad[1]:
             dw = _wgrad(x_buf, cin, dv_buf, cout, kh, kw, pad)
-        if has_bias and ctx.needs_input_grad[2]:
-            db = dv_buf[..., :cout].float().sum((0, 1, 2))
         if has_res and ctx.needs_input_grad[3]:
             dres = dv_buf
         return dx, dw, db, dres, None, None, None, None
@@ -290,7 +296,7 @@ def _s2d_weight_t(w):
     return wp.permute(0, 3, 5, 1, 2, 4).reshape(cout, 4 * cin8, 2, 2)  # channel = (py*2+px)*cin8 + ci, taps (ty,tx)
 
 
-def discriminator_forward_train(D, input_nchw, need_wgrad=True):
+def discriminator_forward_train(D, input_nchw, need_wgrad=True, as_float=True):
     """MultiscaleDiscriminator.forward with autograd (network_generator.py:293-316); returns NCHW fp32 feature lists."""
     x = FromNCHW.apply(input_nchw, None, None)
     cin = input_nchw.shape[1]
@@ -302,7 +308,8 @@ def discriminator_forward_train(D, input_nchw, need_wgrad=True):
         feats = []
         for o in outs:
             c = o.shape[3] if o.dtype != torch.float32 else 1
-            feats.append(o[..., :c].permute(0, 3, 1, 2).float())
+            v = o[..., :c].permute(0, 3, 1, 2)  # NCHW view of the pixel-major buffer (no copy)
+            feats.append(v.float() if as_float else v)
         result.append(feats if not D.no_ganFeat_loss else [feats[-1]])
         if k + 1 < len(ds):
             v = cur[..., :cin].permute(0, 3, 1, 2).float().contiguous()

@@ -265,3 +265,62 @@ extern "C" int hrv_norm_bwd_apply(const hrv_tensor* dxn, const hrv_tensor* src, 
   if (e != cudaSuccess) return set_error(HRV_ECUDA, "norm_bwd_apply launch: %s", cudaGetErrorString(e));
   return HRV_OK;
 }
+
+// ------------------------------------------------------------------------------------------------ activation backward + bias gradient
+namespace hrv {
+// dv = dy * act'(y) (bf16, NHWC) and bias_grad[c] += sum over all pixels of dv — one pass instead of where() + float() + sum().
+__global__ void __launch_bounds__(256) act_bwd_bias_kernel(NView dy, NView y, NView dv, int act, int G, int PL, int chunk,
+                                                          long long npix, double* __restrict__ bsum) {
+  extern __shared__ float shf[];  // [PL][C]
+  const int C = G * 8;
+  const int g = threadIdx.x % G;
+  const int pl = threadIdx.x / G;
+  if (pl < PL) {
+    const int c0 = g * 8;
+    const long long p_begin = (long long)blockIdx.x * chunk;
+    long long p_end = p_begin + chunk;
+    if (p_end > npix) p_end = npix;
+    float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (long long p = p_begin + pl; p < p_end; p += PL) {
+      float fd[8], fy[8], o[8];
+      un8(ld16(reinterpret_cast<const __nv_bfloat16*>(dy.ptr) + p * dy.pitch + c0), fd);
+      if (act != 0) un8(ld16(reinterpret_cast<const __nv_bfloat16*>(y.ptr) + p * y.pitch + c0), fy);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        o[i] = act != 0 ? act_grad(fd[i], fy[i], act) : fd[i];
+        s[i] += o[i];
+      }
+      if (dv.ptr) *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(dv.ptr)) + p * dv.pitch + c0) = pk8(o);
+    }
+    float* dst = shf + (long long)pl * C + c0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dst[i] = s[i];
+  }
+  __syncthreads();
+  if (bsum) {
+    for (int j = threadIdx.x; j < C; j += blockDim.x) {
+      double t = 0.0;
+      for (int l = 0; l < PL; ++l) t += (double)shf[(long long)l * C + j];
+      atomicAdd(&bsum[j], t);
+    }
+  }
+}
+}  // namespace hrv
+
+extern "C" int hrv_act_bwd_bias(const hrv_tensor* dy, const hrv_tensor* y, int32_t act, const hrv_tensor* dv, double* bias_sum,
+                                hrv_stream stream) {
+  int rc;
+  if ((rc = chk(dy, "act_bwd dy")) || (rc = chk(y, "act_bwd y", act == 0)) || (rc = chk(dv, "act_bwd dv", true))) return rc;
+  const int G = (dy->c + 7) / 8;
+  if (G > 256) return set_error(HRV_EUNSUPPORTED, "act_bwd: more than 2048 channels");
+  const long long npix = (long long)dy->n * dy->h * dy->w;
+  int PL, chunk;
+  unsigned gx;
+  plan(npix, 1, G, PL, chunk, gx);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (bias_sum) cudaMemsetAsync(bias_sum, 0, (size_t)G * 8 * sizeof(double), st);
+  act_bwd_bias_kernel<<<gx, 256, (size_t)PL * G * 8 * sizeof(float), st>>>(mkview(dy), mkview(y), mkview(dv), act, G, PL, chunk, npix, bias_sum);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(HRV_ECUDA, "act_bwd_bias launch: %s", cudaGetErrorString(e));
+  return HRV_OK;
+}

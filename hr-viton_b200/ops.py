@@ -360,3 +360,18 @@ def norm_bwd(dh, h, gamma, x0, x0_shift, x1, noise, noise_scale, mean, rstd, act
                                                      mean.data_ptr(), rstd.data_ptr(), m1.data_ptr(), m2.data_ptr(), ctypes.byref(tdx1),
                                                      _p(dns), _stream()), "norm_bwd_apply(x1)")
     return dgb, dx0, dx1, (dns.float() if dns is not None else None), sums[:, :, 2].sum(0).float(), sums[:, :, 3].sum(0).float()
+
+
+def act_bwd_bias(dy, y, act, want_dv=True, want_bias=True):
+    """(dv Act | dy itself when act is NONE, bias_grad fp32 [c] | None) for an epilogue act(conv + b)."""
+    c8 = round_up(dy.c, 8)
+    dv = Act.empty(dy.n, dy.h, dy.w, dy.c, pitch=dy.pitch) if (want_dv and act != ACT_NONE) else None
+    bsum = torch.empty(c8, dtype=torch.float64, device=dy.buf.device) if want_bias else None
+    if dv is None and bsum is None:
+        return dy, None
+    tdy = dy.ct()
+    ty = y.ct() if (y is not None and act != ACT_NONE) else _NULL
+    tdv = dv.ct() if dv is not None else _NULL
+    with _Timed("act_bwd", dy.n * dy.h * dy.w * dy.c * 2.0 * (3 if dv is not None else 1)):
+        capi.check(capi.lib().hrv_act_bwd_bias(ctypes.byref(tdy), ctypes.byref(ty), act, ctypes.byref(tdv), _p(bsum), _stream()), "act_bwd_bias")
+    return (dv if dv is not None else dy), (bsum[:dy.c].float() if bsum is not None else None)

@@ -82,14 +82,14 @@ class Stage2Trainer:
         # ---------------- generator update (train_generator.py:279-322)
         out = self.G(g_in, parse)
         d_in = torch.cat((torch.cat((parse, out), 1), torch.cat((parse, im), 1)), 0)
-        pred = autograd_g.discriminator_forward_train(self.D, d_in, need_wgrad=False)  # D grads are zeroed before use (:354)
+        pred = autograd_g.discriminator_forward_train(self.D, d_in, need_wgrad=False, as_float=False)  # D grads are zeroed before use (:354)
         pred_fake, pred_real = self._split(pred)
         loss_gan = self.crit_gan(pred_fake, True, for_discriminator=False)
         loss_feat = 0
         num_d = len(pred_fake)
         for i in range(num_d):
             for j in range(len(pred_fake[i]) - 1):
-                loss_feat = loss_feat + F.l1_loss(pred_fake[i][j], pred_real[i][j].detach()) * self.lambda_feat / num_d
+                loss_feat = loss_feat + (pred_fake[i][j] - pred_real[i][j].detach()).abs().mean(dtype=torch.float32) * self.lambda_feat / num_d
         loss_vgg = autograd_g.vgg_loss(self.vgg, self.vgg_weights, out, im) * self.lambda_vgg
         loss_gen = (loss_gan + loss_feat + loss_vgg).mean()
         self.opt_g.zero_grad(set_to_none=True)
@@ -101,7 +101,7 @@ class Stage2Trainer:
         with torch.no_grad():
             out2 = self.G(g_in, parse)
         d_in = torch.cat((torch.cat((parse, out2), 1), torch.cat((parse, im), 1)), 0)
-        pred = autograd_g.discriminator_forward_train(self.D, d_in, need_wgrad=True)
+        pred = autograd_g.discriminator_forward_train(self.D, d_in, need_wgrad=True, as_float=False)
         pred_fake, pred_real = self._split(pred)
         loss_dis = (self.crit_gan(pred_fake, False, for_discriminator=True) + self.crit_gan(pred_real, True, for_discriminator=True)).mean()
         self.opt_d.zero_grad(set_to_none=True)

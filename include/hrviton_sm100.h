@@ -114,6 +114,11 @@ int hrv_norm_bwd_apply(const hrv_tensor* dxn, const hrv_tensor* src, int32_t shi
                        int32_t W, const float* noise, const float* noise_scale, const float* mean, const float* rstd,
                        const float* m1, const float* m2, const hrv_tensor* dx, double* dns, hrv_stream stream);
 
+/* dv = dy * act'(y) on NHWC bf16 (dv optional) and bias_sum[c] = sum over all pixels of dv (fp64 [roundup8(C)], zeroed by the
+ * call; optional): the activation backward + bias gradient of a conv epilogue act(conv + b) in one pass. */
+int hrv_act_bwd_bias(const hrv_tensor* dy, const hrv_tensor* y, int32_t act, const hrv_tensor* dv, double* bias_sum,
+                     hrv_stream stream);
+
 /* fp32 NCHW -> bf16 NHWC with nearest resampling to (dst.h, dst.w): src index = floor(dst*in/out)
  * (F.interpolate(mode='nearest'), network_generator.py:164,222) and zero fill of dst channels >= C.
  * src: [n][c][src_h][src_w] fp32 contiguous. */
