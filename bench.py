@@ -317,11 +317,13 @@ def main():
             ms = float(t.item())
         return ms
 
-    for _ in range(W_):
-        step_resident()
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.start()  # started before the warm-up: nvidia-smi needs ~0.5 s to emit its first sample
+    for _ in range(W_):
+        step_resident()
+    if rank == 0:
+        sampler.lines.clear()  # keep only samples taken during the timed region
     l0 = ops.LAUNCHES[0]
     ms = timed(step_resident, K)
     launches = ops.LAUNCHES[0] - l0
