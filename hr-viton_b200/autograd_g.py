@@ -4,8 +4,7 @@ torch.autograd carries the graph; every node is a fused C-ABI op on pixel-major 
 
   ConvFn    y = act(conv(x, W) * 1 + b (+ res))          fwd: hrv_conv2d_fwd
             dX  = conv(dY', flip(W)^T)                     bwd: hrv_conv2d_fwd again (dgrad IS a convolution)
-            dW  = x^T (*) dY'                              bwd: hrv_conv2d_wgrad (tcgen05) when available, else the cuDNN
-                                                                weight-gradient as a staged stand-in
+            dW  = x^T (*) dY'                              bwd: hrv_conv2d_wgrad (tcgen05, pixel-K GEMM with MN-major operands)
   SpadeFn   h = act(IN(cat(up(x0),x1) + noise*ns) * (1+gamma(actv)) + beta(actv))
             fwd: hrv_instnorm_stats + hrv_conv2d_fwd(SPADE epilogue); bwd: modulation / InstanceNorm backward +
             dgrad/wgrad of the gamma|beta GEMM.
@@ -13,6 +12,8 @@ torch.autograd carries the graph; every node is a fused C-ABI op on pixel-major 
 Spectral norm stays differentiable in torch (W/sigma with sigma = u.(W v), tiny weight-sized tensors), exactly as the
 reference's old-style torch.nn.utils.spectral_norm does (network_generator.py:138-143).
 """
+import os
+
 import torch
 import torch.nn.functional as F
 
@@ -36,11 +37,13 @@ def _act_grad(dy, y, act):
 
 
 def _wgrad(x_buf, cin, dy_buf, cout, kh, kw, pad):
-    """dW (cout,cin,kh,kw) fp32 = sum over pixels of dY[p,co] * X[p+tap-pad,ci].  Staged implementation: cuDNN's
-    weight-gradient on channels-last views (library call; replaced by hrv_conv2d_wgrad in the kernel roadmap)."""
-    x = x_buf[..., :cin].permute(0, 3, 1, 2)
-    dy = dy_buf[..., :cout].permute(0, 3, 1, 2)
-    return torch.nn.grad.conv2d_weight(x, (cout, cin, kh, kw), dy, stride=1, padding=pad).float()
+    """dW (cout,cin,kh,kw) fp32 = sum over pixels of dY[p,co] * X[p+tap-pad,ci] on tcgen05 (hrv_conv2d_wgrad).
+    HRV_WGRAD=cudnn selects the library weight-gradient instead (A/B comparisons only)."""
+    if os.environ.get("HRV_WGRAD") == "cudnn":
+        x = x_buf[..., :cin].permute(0, 3, 1, 2)
+        dy = dy_buf[..., :cout].permute(0, 3, 1, 2)
+        return torch.nn.grad.conv2d_weight(x, (cout, cin, kh, kw), dy, stride=1, padding=pad).float()
+    return ops.conv2d_wgrad(Act(x_buf, c=cin), Act(dy_buf, c=cout), kh, kw, pad)
 
 
 class ConvFn(torch.autograd.Function):

@@ -375,3 +375,13 @@ def act_bwd_bias(dy, y, act, want_dv=True, want_bias=True):
     with _Timed("act_bwd", dy.n * dy.h * dy.w * dy.c * 2.0 * (3 if dv is not None else 1)):
         capi.check(capi.lib().hrv_act_bwd_bias(ctypes.byref(tdy), ctypes.byref(ty), act, ctypes.byref(tdv), _p(bsum), _stream()), "act_bwd_bias")
     return (dv if dv is not None else dy), (bsum[:dy.c].float() if bsum is not None else None)
+
+
+def conv2d_wgrad(x, dy, kh, kw, pad):
+    """dW (cout,cin,kh,kw) fp32 of a stride-1 convolution, on tcgen05 (hrv_conv2d_wgrad)."""
+    dw = torch.zeros((dy.c, x.c, kh, kw), dtype=torch.float32, device=x.buf.device)
+    tx, tdy = x.ct(), dy.ct()
+    with _Timed("wgrad", 2.0 * x.c * dy.c * kh * kw * dy.n * dy.h * dy.w,
+                label="%d->%d k%dx%d n%d %dx%d" % (x.c, dy.c, kh, kw, dy.n, dy.h, dy.w)):
+        capi.check(capi.lib().hrv_conv2d_wgrad(ctypes.byref(tx), ctypes.byref(tdy), kh, kw, pad, dw.data_ptr(), _stream()), "conv2d_wgrad")
+    return dw

@@ -114,6 +114,12 @@ int hrv_norm_bwd_apply(const hrv_tensor* dxn, const hrv_tensor* src, int32_t shi
                        int32_t W, const float* noise, const float* noise_scale, const float* mean, const float* rstd,
                        const float* m1, const float* m2, const hrv_tensor* dx, double* dns, hrv_stream stream);
 
+/* Convolution weight gradient on tcgen05: dw[co][ci][ky][kx] += sum_{n,y,x} dy[n,y,x,co] * x[n,y+ky-pad,x+kx-pad,ci]
+ * (stride 1; x: (n,h,w,cin), dy: (n,h+2pad-kh+1, w+2pad-kw+1, cout), both bf16 NHWC; kw <= 4). dw is fp32 in the reference's
+ * parameter layout (cout,cin,kh,kw) and must be zeroed by the caller (partial tiles are accumulated with atomic adds).
+ * The weight-gradient half of nn.Conv2d's backward for every convolution cited at hrv_conv2d_fwd. */
+int hrv_conv2d_wgrad(const hrv_tensor* x, const hrv_tensor* dy, int32_t kh, int32_t kw, int32_t pad, float* dw, hrv_stream stream);
+
 /* dv = dy * act'(y) on NHWC bf16 (dv optional) and bias_sum[c] = sum over all pixels of dv (fp64 [roundup8(C)], zeroed by the
  * call; optional): the activation backward + bias gradient of a conv epilogue act(conv + b) in one pass. */
 int hrv_act_bwd_bias(const hrv_tensor* dy, const hrv_tensor* y, int32_t act, const hrv_tensor* dv, double* bias_sum,

@@ -225,3 +225,23 @@ def test_flow_warp_bit_exact(c, src_fp32):
     assert rel_err(got, ref) < (1e-5 if src_fp32 else 1e-2)
     # and against the torch substrate the reference actually calls
     assert rel_err(got, orc.flow_warp(src_used, flow)) < (1e-4 if src_fp32 else 1e-2)
+
+
+WGRAD_CASES = [(2, 64, 128, 24, 16, 3, 1), (1, 128, 160, 32, 24, 3, 1), (2, 80, 32, 64, 48, 3, 1), (1, 7, 128, 32, 24, 3, 1),
+               (1, 1040, 512, 16, 12, 3, 1), (2, 96, 384, 16, 12, 1, 0), (2, 64, 24, 17, 13, 2, 1), (1, 256, 1, 17, 13, 4, 2),
+               (1, 32, 3, 128, 96, 3, 1), (2, 128, 288, 130, 70, 3, 1)]
+
+
+@pytest.mark.parametrize("case", WGRAD_CASES, ids=lambda c: "n%d_%dto%d_%dx%d_k%dp%d" % c)
+def test_conv_wgrad(case):
+    """hrv_conv2d_wgrad vs torch's fp32 weight gradient of the same (bf16-rounded) operands."""
+    n, cin, cout, h, w, k, pad = case
+    x = bf16r(synth.normalish((n, cin, h, w), 21, "x"))
+    oh, ow = h + 2 * pad - k + 1, w + 2 * pad - k + 1
+    dy = bf16r(synth.normalish((n, cout, oh, ow), 21, "dy"))
+    ref = torch.nn.grad.conv2d_weight(x, (cout, cin, k, k), dy, stride=1, padding=pad)
+    got = ops.conv2d_wgrad(ops.from_nchw(x.to(DEV)), ops.from_nchw(dy.to(DEV)), k, k, pad)
+    torch.cuda.synchronize()
+    err = rel_err(got, ref)
+    print("wgrad rel err", case, err)
+    assert err < 2e-3
