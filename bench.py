@@ -9,6 +9,8 @@ Prints ONE JSON line on rank 0.  Workloads (config.workload):
   train_stage2  (default) one full train_generator.py step per "step": frozen tocg -> warp -> SPADE G fwd+bwd -> D fwd+bwd
                 (hinge + feature matching) + VGG loss -> Adam(G), then the D update (2nd G fwd, D fwd+bwd, Adam(D)),
                 1024x768, bf16 activations (BASELINE.json configs[3], per-GPU batch --batch)
+  train_stage1  one full train_condition.py step (tocg fwd+bwd with train-mode BatchNorm, stage-1 D, L1+VGG+TV+CE+LSGAN, Adam x2),
+                1024x768 per-GPU batch 4 (BASELINE.json configs[1])
   gen_fwd       SPADEGenerator inference forward, 1024x768, per-GPU batch 8 (BASELINE.json configs[2])
 """
 import argparse
@@ -213,8 +215,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: 4 for train_stage2, 8 for gen_fwd)")
-    ap.add_argument("--workload", default="train_stage2", choices=["train_stage2", "gen_fwd"])
+    ap.add_argument("--workload", default="train_stage2", choices=["train_stage2", "train_stage1", "gen_fwd"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="train_stage2: launch eagerly instead of replaying a CUDA graph")
     ap.add_argument("--dump-profile", default="", help="write the per-launch CUDA-event profile of one step as CSV")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -236,7 +239,8 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     W_ = max(3, args.warmup)
     K = args.steps
-    train = args.workload == "train_stage2"
+    train = args.workload in ("train_stage2", "train_stage1")
+    stage1 = args.workload == "train_stage1"
     B = args.batch or (4 if train else 8)
 
     def barrier():
@@ -258,30 +262,71 @@ def main():
                     mod.running_mean.normal_(0, 0.1)
                     mod.running_var.uniform_(0.5, 1.5)
         tocg = tocg.to(dev).eval()
-        g = build_generator(dev).train()
+        g = None if stage1 else build_generator(dev).train()
         dopt = gen_opt()
         dopt.ndf, dopt.norm_D, dopt.n_layers_D, dopt.num_D, dopt.no_ganFeat_loss = 64, "spectralinstance", 3, 2, False
-        D = network_generator.MultiscaleDiscriminator(dopt)
-        D.init_weights("xavier", 0.02)
-        D = D.to(dev).train()
         vgg = networks.Vgg19().to(dev).eval()
         reducers = {}
-        if world > 1:
-            reducers = {"G": ddp.GradBucketReducer(list(g.parameters())), "D": ddp.GradBucketReducer(list(D.parameters()))}
-        trainer = train_step.Stage2Trainer(tocg, g, D, vgg, reducers=reducers)
-        batch_h = {k: v.pin_memory() for k, v in train_step.synthetic_batch(B, H, W, "cpu", seed=100 + rank).items()}
+        if stage1:
+            import contextlib
+            import io
+            tocg.train()
+            with contextlib.redirect_stdout(io.StringIO()):
+                D = networks.define_D(input_nc=33, Ddownx2=True, Ddropout=True, n_layers_D=3, spectral=False, num_D=2)
+            D = D.to(dev).train()
+            if world > 1:
+                reducers = {"G": ddp.GradBucketReducer(list(tocg.parameters())), "D": ddp.GradBucketReducer(list(D.parameters()))}
+            tr1 = train_step.Stage1Trainer(tocg, D, vgg, reducers=reducers)
+
+            class _Shim:  # same step/capture/replay surface as Stage2Trainer
+                def step(self, b, h, w):
+                    return tr1.step(b)
+
+                def capture(self, b, h, w):
+                    raise RuntimeError("stage-1 step is launched eagerly (Dropout RNG + BatchNorm counters are not graph-captured yet)")
+            trainer = _Shim()
+            make_batch = train_step.synthetic_batch_stage1
+        else:
+            D = network_generator.MultiscaleDiscriminator(dopt)
+            D.init_weights("xavier", 0.02)
+            D = D.to(dev).train()
+            if world > 1:
+                reducers = {"G": ddp.GradBucketReducer(list(g.parameters())), "D": ddp.GradBucketReducer(list(D.parameters()))}
+            trainer = train_step.Stage2Trainer(tocg, g, D, vgg, reducers=reducers)
+            make_batch = train_step.synthetic_batch
+        batch_h = {k: v.pin_memory() for k, v in make_batch(B, H, W, "cpu", seed=100 + rank).items()}
         batch_d = {k: v.to(dev) for k, v in batch_h.items()}
         loss_h = torch.empty(2, dtype=torch.float32).pin_memory()
         h2d_bytes = int(sum(v.numel() * v.element_size() for v in batch_h.values()))
         d2h_bytes = 8
 
+        use_graph = not args.no_graph and not stage1
+        if use_graph:
+            try:
+                trainer.step(batch_d, H, W)  # first eager step: lazy initialisation (optimizer state, func attributes, caches)
+                l_cap = ops.LAUNCHES[0]
+                trainer.capture(batch_d, H, W)
+                launches_per_replay = (ops.LAUNCHES[0] - l_cap) // 3  # capture() runs 2 warm steps + the captured one
+            except Exception as e:  # noqa: BLE001 - report and fall back to eager launches
+                import traceback
+                sys.stderr.write("CUDA graph capture failed (%s: %s); running eagerly\n%s\n" % (type(e).__name__, e, traceback.format_exc()[-1500:]))
+                use_graph = False
+
         def step_resident():
+            if use_graph:
+                ops.LAUNCHES[0] += launches_per_replay
+                return trainer.replay()
             return trainer.step(batch_d, H, W)
 
         def step_e2e():
-            bd = {k: v.to(dev, non_blocking=True) for k, v in batch_h.items()}
-            out = trainer.step(bd, H, W)
-            loss_h.copy_(torch.stack([out["loss_gen"].float(), out["loss_dis"].float()]), non_blocking=True)
+            if use_graph:
+                ops.LAUNCHES[0] += launches_per_replay
+                out = trainer.replay(batch_h)
+            else:
+                bd = {k: v.to(dev, non_blocking=True) for k, v in batch_h.items()}
+                out = trainer.step(bd, H, W)
+            lk = ("loss_g", "loss_d") if stage1 else ("loss_gen", "loss_dis")
+            loss_h.copy_(torch.stack([out[lk[0]].float(), out[lk[1]].float()]), non_blocking=True)
     else:
         g = build_generator(dev)
         x_h, seg_h = synth_batch(B, "cpu", 100 + rank)
@@ -338,7 +383,10 @@ def main():
     # ---- per-kernel profile pass (CUDA events around every C-ABI launch) -> roofline of the dominant kernel
     ops.PROFILE = []
     torch.cuda.synchronize()
-    step_resident()
+    if train:
+        trainer.step(batch_d, H, W)  # eager (events cannot be recorded inside a graph replay)
+    else:
+        step_resident()
     torch.cuda.synchronize()
     prof = ops.PROFILE
     ops.PROFILE = None
@@ -379,15 +427,16 @@ def main():
         line = {"metric": "1024x768 try-on images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W_,
                 "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
                 "data": "synthetic",
-                "config": {"workload": ("train_stage2: full train_generator.py step (tocg fwd, G fwd+bwd, D fwd+bwd x2, 2nd G fwd, VGG loss fwd+dgrad, Adam x2), 1024x768, bf16 activations / fp32 accumulate; conv wgrad still via cuDNN (staged), everything else on this repo's kernels or torch glue"
+                "config": {"workload": ("train_stage1: full train_condition.py step (tocg fwd+bwd with train-mode BatchNorm, 3 stage-1 D passes fwd+bwd, VGG loss x5 fwd+dgrad, L1/TV/CE/LSGAN, Adam x2; README flags --Ddownx2 --Ddropout --lasttvonly --interflowloss --occlusion), 1024x768, bf16 activations / fp32 accumulate" if (train and stage1) else
+                                        "train_stage2: full train_generator.py step (tocg fwd, G fwd+bwd, D fwd+bwd x2, 2nd G fwd, VGG loss fwd+dgrad, Adam x2), 1024x768, bf16 activations / fp32 accumulate; convs (fwd/dgrad/wgrad), norms, modulation, activations on this repo's kernels; resampling glue, max-pool, losses, Adam = torch"
                                         if train else "gen_fwd: SPADEGenerator inference forward, 1024x768, bf16 activations, fp32 accumulate"),
-                           "per_gpu_batch": B, "global_batch": B * world, "parallelism": "dp%d" % world,
+                           "launch": ("cuda-graph replay of the whole step" if (train and use_graph) else "eager"), "per_gpu_batch": B, "global_batch": B * world, "parallelism": "dp%d" % world,
                            "l2": "activations per step (>10 GB) exceed the 126 MB L2; no explicit flush",
                            "weights": "xavier(0.02) random init, noise_scale~N(0,0.1)"},
                 "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": ms_e2e / K,
                         "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernel_breakdown": breakdown,
-                "model_tflops": (8800.0 if train else GEN_GFLOP_PER_IMG) * value / 1e3}
+                "model_tflops": (None if stage1 else (8800.0 if train else GEN_GFLOP_PER_IMG) * value / 1e3)}
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
         print(json.dumps(line))

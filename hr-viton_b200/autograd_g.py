@@ -290,7 +290,10 @@ def _nlayer_train(d, x_buf, need_wgrad):
 
 
 def _s2d_weight_t(w):
-    """Differentiable version of ops.s2d_weight for k=4, pad=2 (index shuffle only)."""
+    """Differentiable version of ops.s2d_weight (index shuffle only): k=4/pad=2, or k=3/pad=1 embedded in a 4x4 kernel with a
+    zero first row/column (tap ky of the 3x3 sits at ky+1)."""
+    if w.shape[2] == 3:
+        w = F.pad(w, (1, 0, 1, 0))
     cout, cin, k, _ = w.shape
     assert k == 4
     cin8 = ops.round_up(cin, 8)

@@ -11,7 +11,7 @@ ACT_NONE, ACT_RELU, ACT_LRELU, ACT_TANH = 0, 1, 2, 3
 NHWC, NCHW = 0, 1
 EPI_LINEAR, EPI_SPADE = 0, 1
 
-EXPORTS = ["hrv_conv2d_fwd", "hrv_instnorm_stats", "hrv_instnorm_apply", "hrv_norm_bwd_reduce", "hrv_norm_bwd_apply", "hrv_act_bwd_bias", "hrv_conv2d_wgrad", "hrv_nchw_to_nhwc", "hrv_nhwc_to_nchw",
+EXPORTS = ["hrv_conv2d_fwd", "hrv_instnorm_stats", "hrv_instnorm_apply", "hrv_norm_apply_affine", "hrv_norm_bwd_reduce", "hrv_norm_bwd_apply", "hrv_act_bwd_bias", "hrv_conv2d_wgrad", "hrv_nchw_to_nhwc", "hrv_nhwc_to_nchw",
            "hrv_space_to_depth", "hrv_avgpool3s2", "hrv_bilinear_up2_add", "hrv_flow_warp", "hrv_last_error",
            "hrv_version", "hrv_device_sm_count"]
 
@@ -48,7 +48,8 @@ def lib():
     L.hrv_conv2d_fwd.argtypes = [ctypes.POINTER(ConvParams), vp]
     L.hrv_instnorm_stats.argtypes = [TP, i32, TP, i32, i32, vp, vp, f32, vp, vp, vp, ctypes.c_size_t, vp]
     L.hrv_instnorm_apply.argtypes = [TP, vp, vp, i32, TP, vp]
-    L.hrv_norm_bwd_reduce.argtypes = [TP, TP, TP, TP, i32, TP, i32, i32, vp, vp, vp, vp, i32, TP, TP, vp, vp]
+    L.hrv_norm_bwd_reduce.argtypes = [TP, TP, TP, TP, i32, TP, i32, i32, vp, vp, vp, vp, vp, i32, TP, TP, vp, vp]
+    L.hrv_norm_apply_affine.argtypes = [TP, vp, vp, vp, vp, TP, i32, TP, vp]
     L.hrv_norm_bwd_apply.argtypes = [TP, TP, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, TP, vp, vp]
     L.hrv_act_bwd_bias.argtypes = [TP, TP, i32, TP, vp, vp]
     L.hrv_conv2d_wgrad.argtypes = [TP, TP, i32, i32, i32, vp, vp]

@@ -127,21 +127,30 @@ __global__ void instnorm_finalize_kernel(const double* __restrict__ acc, int NC,
   rstd[i] = (float)(1.0 / sqrt(var + (double)eps));
 }
 
-__global__ void instnorm_apply_kernel(View x, const float* __restrict__ mean, const float* __restrict__ rstd, int act, View y,
+__global__ void instnorm_apply_kernel(View x, const float* __restrict__ mean, const float* __restrict__ rstd,
+                                      const float* __restrict__ gamma, const float* __restrict__ beta, View res, int act, View y,
                                       long long total, int G) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int g = (int)(idx % G);
   const long long pix = idx / G;
   const int n = (int)(pix / ((long long)x.h * x.w));
-  float f[8];
+  float f[8], r[8];
   unpack8(ldg16(reinterpret_cast<const __nv_bfloat16*>(x.ptr) + pix * x.pitch + g * 8), f);
+  if (res.ptr) unpack8(ldg16(reinterpret_cast<const __nv_bfloat16*>(res.ptr) + pix * res.pitch + g * 8), r);
   const float* mp = mean + (long long)n * x.c + g * 8;
   const float* rp = rstd + (long long)n * x.c + g * 8;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const bool in = g * 8 + i < x.c;
-    f[i] = in ? apply_act((f[i] - __ldg(mp + i)) * __ldg(rp + i), act) : 0.f;
+    const int c = g * 8 + i;
+    if (c < x.c) {
+      float v = (f[i] - __ldg(mp + i)) * __ldg(rp + i);
+      if (gamma) v = fmaf(v, __ldg(gamma + c), beta ? __ldg(beta + c) : 0.f);
+      if (res.ptr) v += r[i];
+      f[i] = apply_act(v, act);
+    } else {
+      f[i] = 0.f;
+    }
   }
   *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(y.ptr)) + pix * y.pitch + g * 8) = pack8(f);
 }
@@ -404,14 +413,23 @@ extern "C" int hrv_instnorm_stats(const hrv_tensor* x0, int32_t x0_shift, const 
   return launch_ok("instnorm_finalize");
 }
 
-extern "C" int hrv_instnorm_apply(const hrv_tensor* x, const float* mean, const float* rstd, int32_t act, const hrv_tensor* y,
-                                  hrv_stream stream) {
+extern "C" int hrv_norm_apply_affine(const hrv_tensor* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                                     const hrv_tensor* res, int32_t act, const hrv_tensor* y, hrv_stream stream) {
   int rc;
-  if ((rc = check_bf16_vec(x, "instnorm_apply x")) || (rc = check_bf16_vec(y, "instnorm_apply y"))) return rc;
+  if ((rc = check_bf16_vec(x, "norm_apply x")) || (rc = check_bf16_vec(y, "norm_apply y"))) return rc;
+  const bool hr = res && res->ptr;
+  if (hr && (rc = check_bf16_vec(res, "norm_apply res"))) return rc;
+  if (!mean || !rstd) return set_error(HRV_EINVAL, "norm_apply: mean/rstd required");
   const int G = (x->c + 7) / 8;
   const long long total = (long long)x->n * x->h * x->w * G;
-  instnorm_apply_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(mk(x), mean, rstd, act, mk(y), total, G);
-  return launch_ok("instnorm_apply");
+  instnorm_apply_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(mk(x), mean, rstd, gamma, beta, mk(hr ? res : nullptr), act,
+                                                                                 mk(y), total, G);
+  return launch_ok("norm_apply");
+}
+
+extern "C" int hrv_instnorm_apply(const hrv_tensor* x, const float* mean, const float* rstd, int32_t act, const hrv_tensor* y,
+                                  hrv_stream stream) {
+  return hrv_norm_apply_affine(x, mean, rstd, nullptr, nullptr, nullptr, act, y, stream);
 }
 
 extern "C" int hrv_nchw_to_nhwc(const float* src, int32_t c, int32_t src_h, int32_t src_w, const hrv_tensor* dst, hrv_stream stream) {

@@ -51,6 +51,7 @@ struct BwdArgs {
   const float* ns;
   const float* mean;
   const float* rstd;
+  const float* chan_scale;  // optional per-channel affine weight (BatchNorm): dxn = dv * chan_scale[c]
   double* acc;  // [N][C][4]
 };
 
@@ -67,10 +68,11 @@ __global__ void __launch_bounds__(256) spade_bwd_reduce_kernel(BwdArgs a) {
     const long long p_begin = (long long)blockIdx.x * a.chunk;
     long long p_end = p_begin + a.chunk;
     if (p_end > HW) p_end = HW;
-    float s1[8], s2[8], sg[8], sb[8], nsv[8], mu[8], rs[8];
+    float s1[8], s2[8], sg[8], sb[8], nsv[8], mu[8], rs[8], cs[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       s1[i] = s2[i] = sg[i] = sb[i] = 0.f;
+      cs[i] = a.chan_scale ? __ldg(a.chan_scale + c0 + i) : 1.f;
       nsv[i] = a.ns ? __ldg(a.ns + c0 + i) : 0.f;
       mu[i] = __ldg(a.mean + (long long)n * C + c0 + i);
       rs[i] = __ldg(a.rstd + (long long)n * C + c0 + i);
@@ -96,7 +98,7 @@ __global__ void __launch_bounds__(256) spade_bwd_reduce_kernel(BwdArgs a) {
         const float dv = a.act != 0 ? act_grad(fdh[i], fh[i], a.act) : fdh[i];
         dgm[i] = dv * xn;
         dbt[i] = dv;
-        dxn[i] = a.gamma.ptr ? dv * (1.f + fg[i]) : dv;
+        dxn[i] = a.gamma.ptr ? dv * (1.f + fg[i]) : dv * cs[i];
         s1[i] += dxn[i];
         s2[i] = fmaf(dxn[i], xn, s2[i]);
         sg[i] += dgm[i];
@@ -220,7 +222,7 @@ using namespace hrv;
 
 extern "C" int hrv_norm_bwd_reduce(const hrv_tensor* dh, const hrv_tensor* h, const hrv_tensor* gamma, const hrv_tensor* x0,
                                    int32_t x0_shift, const hrv_tensor* x1, int32_t H, int32_t W, const float* noise,
-                                   const float* noise_scale, const float* mean, const float* rstd, int32_t act,
+                                   const float* noise_scale, const float* mean, const float* rstd, const float* chan_scale, int32_t act,
                                    const hrv_tensor* dgb, const hrv_tensor* dxn, double* sums, hrv_stream stream) {
   int rc;
   if ((rc = chk(dh, "norm_bwd dh")) || (rc = chk(x0, "norm_bwd x0")) || (rc = chk(dxn, "norm_bwd dxn")) || (rc = chk(h, "norm_bwd h", act == 0)) ||
@@ -235,7 +237,7 @@ extern "C" int hrv_norm_bwd_reduce(const hrv_tensor* dh, const hrv_tensor* h, co
   BwdArgs a;
   a.dh = mkview(dh); a.h = mkview(h); a.gamma = mkview(gamma); a.x0 = mkview(x0); a.x1 = mkview(has1 ? x1 : nullptr); a.dgb = mkview(dgb); a.dxn = mkview(dxn);
   a.x0_shift = x0_shift; a.H = H; a.W = W; a.G = C / 8; a.act = act;
-  a.noise = noise; a.ns = noise_scale; a.mean = mean; a.rstd = rstd; a.acc = sums;
+  a.noise = noise; a.ns = noise_scale; a.mean = mean; a.rstd = rstd; a.chan_scale = chan_scale; a.acc = sums;
   unsigned gx;
   plan((long long)H * W, N, a.G, a.PL, a.chunk, gx);
   cudaStream_t st = (cudaStream_t)stream;

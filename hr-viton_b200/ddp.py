@@ -17,6 +17,7 @@ class GradBucketReducer:
         self.params = [p for p in params if p.requires_grad]
         self.bucket_bytes = bucket_bytes
         self.group = group
+        self._present = None
 
     def reduce(self):
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.group) == 1:
@@ -25,9 +26,11 @@ class GradBucketReducer:
         if not self.params:
             return 0
         dev = self.params[0].device
-        mask = torch.tensor([1 if p.grad is not None else 0 for p in self.params], dtype=torch.int32, device=dev)
-        dist.all_reduce(mask, op=dist.ReduceOp.MAX, group=self.group)
-        present = mask.tolist()
+        if self._present is None:  # decided once (the set of parameters that receive gradients is static): keeps later calls
+            mask = torch.tensor([1 if p.grad is not None else 0 for p in self.params], dtype=torch.int32, device=dev)  # sync-free
+            dist.all_reduce(mask, op=dist.ReduceOp.MAX, group=self.group)
+            self._present = mask.tolist()
+        present = self._present
         buckets, cur, cur_bytes = [], [], 0
         for p, has in zip(self.params, present):
             if not has:

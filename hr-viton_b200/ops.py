@@ -321,7 +321,7 @@ def flow_warp(flow_lo, src, dst, want_flow_up=True, want_idx=False):
     return flow_up, idx
 
 
-def norm_bwd(dh, h, gamma, x0, x0_shift, x1, noise, noise_scale, mean, rstd, act, want_dgb):
+def norm_bwd(dh, h, gamma, x0, x0_shift, x1, noise, noise_scale, mean, rstd, act, want_dgb, chan_scale=None, batch_stats=False):
     """Fused backward of the SPADE modulation + InstanceNorm (gamma given) or of InstanceNorm + activation (gamma None).
     Returns (dgb Act | None, dx0 Act, dx1 Act | None, d_noise_scale fp32 [C] | None, sum_dgamma fp32 [C], sum_dbeta fp32 [C])."""
     n, H, W = dh.n, dh.h, dh.w
@@ -340,10 +340,15 @@ def norm_bwd(dh, h, gamma, x0, x0_shift, x1, noise, noise_scale, mean, rstd, act
     with _Timed("norm_bwd", n * H * W * C * 2.0 * (4 + (1 if gamma is not None else 0) + (2 if want_dgb else 0)), launches=2):
         capi.check(capi.lib().hrv_norm_bwd_reduce(ctypes.byref(tdh), ctypes.byref(th), ctypes.byref(tg), ctypes.byref(tx0), x0_shift,
                                                   ctypes.byref(tx1), H, W, _p(noise), _p(noise_scale), mean.data_ptr(), rstd.data_ptr(),
-                                                  act, ctypes.byref(tdgb), ctypes.byref(tdxn), sums.data_ptr(), _stream()), "norm_bwd_reduce")
-    inv = 1.0 / float(H * W)
-    m1 = (sums[:, :, 0] * inv).float().contiguous()
-    m2 = (sums[:, :, 1] * inv).float().contiguous()
+                                                  _p(chan_scale), act, ctypes.byref(tdgb), ctypes.byref(tdxn), sums.data_ptr(), _stream()), "norm_bwd_reduce")
+    if batch_stats:  # BatchNorm: the two means run over (N,H,W)
+        tot = sums.sum(0, keepdim=True) / float(n * H * W)
+        m1 = tot[:, :, 0].expand(n, C).float().contiguous()
+        m2 = tot[:, :, 1].expand(n, C).float().contiguous()
+    else:
+        inv = 1.0 / float(H * W)
+        m1 = (sums[:, :, 0] * inv).float().contiguous()
+        m2 = (sums[:, :, 1] * inv).float().contiguous()
     dns = torch.zeros(C, dtype=torch.float64, device=dev) if noise_scale is not None else None
     dx0 = Act.empty(n, x0.h, x0.w, c0)
     tdx0 = dx0.ct()
@@ -385,3 +390,31 @@ def conv2d_wgrad(x, dy, kh, kw, pad):
                 label="%d->%d k%dx%d n%d %dx%d" % (x.c, dy.c, kh, kw, dy.n, dy.h, dy.w)):
         capi.check(capi.lib().hrv_conv2d_wgrad(ctypes.byref(tx), ctypes.byref(tdy), kh, kw, pad, dw.data_ptr(), _stream()), "conv2d_wgrad")
     return dw
+
+
+def batchnorm_stats(x, eps=1e-5):
+    """Train-mode BatchNorm2d statistics over (N,H,W) from ONE pass of the statistics kernel (per-image fp64 partial sums combined
+    here on [N][C] scalars) — the "single-kernel reduce" standing in for SyncBatchNorm.  Returns (mean[C], biased var[C]) fp32."""
+    n, c = x.n, x.c
+    ws = _workspace(n * c * 16, x.buf.device)
+    mean_nc = torch.empty((n, c), dtype=torch.float32, device=x.buf.device)
+    rstd_nc = torch.empty_like(mean_nc)
+    t0 = x.ct()
+    with _Timed("instnorm_stats", n * x.h * x.w * 2.0 * c, launches=3, label="bn c%d n%d %dx%d" % (c, n, x.h, x.w)):
+        capi.check(capi.lib().hrv_instnorm_stats(ctypes.byref(t0), 0, ctypes.byref(_NULL), x.h, x.w, None, None, eps, mean_nc.data_ptr(),
+                                                 rstd_nc.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "batchnorm_stats")
+    sums = ws[: n * c * 16].view(torch.float64).view(n, c, 2).sum(0)  # raw sum / sum of squares left in the workspace
+    cnt = float(n * x.h * x.w)
+    mean = sums[:, 0] / cnt
+    var = (sums[:, 1] / cnt - mean * mean).clamp_min(0.0)
+    return mean.float(), var.float()
+
+
+def norm_apply_affine(x, mean_nc, rstd_nc, gamma, beta, res, act, out=None):
+    out = Act.empty(x.n, x.h, x.w, x.c) if out is None else out
+    tx, ty = x.ct(), out.ct()
+    tr = res.ct() if res is not None else _NULL
+    with _Timed("norm_apply", x.n * x.h * x.w * x.c * 2.0 * (3 if res is not None else 2)):
+        capi.check(capi.lib().hrv_norm_apply_affine(ctypes.byref(tx), mean_nc.data_ptr(), rstd_nc.data_ptr(), _p(gamma), _p(beta),
+                                                    ctypes.byref(tr), act, ctypes.byref(ty), _stream()), "norm_apply_affine")
+    return out

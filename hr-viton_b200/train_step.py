@@ -7,6 +7,7 @@ Hot path = the three networks (kernels of this repo).  The per-step tensor glue 
 import torch
 import torch.nn.functional as F
 
+_GRID_CACHE = {}
 LABELS7 = [[0], [2, 4, 7, 8, 9, 10, 11], [3], [1], [5], [6], [12]]  # train_generator.py:261-269
 
 
@@ -37,7 +38,10 @@ def make_generator_inputs(tocg, batch, fine_h, fine_w, occlusion=False):
         mask[:, 3:4] = warped_cm
         fake_segmap = fake_segmap * mask
         n, _, ih, iw = c_paired.shape
-        grid = make_grid(n, ih, iw).to(c_paired.device)
+        key = (n, ih, iw, str(c_paired.device))
+        if key not in _GRID_CACHE:  # the reference rebuilds this on the CPU and copies it every step (networks.py:162-165)
+            _GRID_CACHE[key] = make_grid(n, ih, iw).to(c_paired.device)
+        grid = _GRID_CACHE[key]
         flow = F.interpolate(flow_list[-1].permute(0, 3, 1, 2), size=(ih, iw), mode="bilinear").permute(0, 2, 3, 1)
         flow_norm = torch.cat([flow[..., 0:1] / ((96 - 1.0) / 2.0), flow[..., 1:2] / ((128 - 1.0) / 2.0)], 3)
         warped_grid = grid + flow_norm
@@ -50,7 +54,13 @@ def make_generator_inputs(tocg, batch, fine_h, fine_w, occlusion=False):
             warped_clothmask = warped_clothmask - torch.cat([so[:, 1:3], so[:, 5:]], 1).sum(1, keepdim=True) * warped_clothmask
             warped_cloth = warped_cloth * warped_clothmask + (1 - warped_clothmask)
         old_parse = torch.zeros(n, 13, fine_h, fine_w, device=cm.device).scatter_(1, fake_parse, 1.0)
-        parse = torch.stack([old_parse[:, idx].sum(1) for idx in LABELS7], 1)
+        mkey = ("regroup", str(cm.device))
+        if mkey not in _GRID_CACHE:  # 13 -> 7 class regrouping as a constant 7x13 0/1 matrix (train_generator.py:261-273)
+            m = torch.zeros(7, 13)
+            for i, idx in enumerate(LABELS7):
+                m[i, idx] = 1.0
+            _GRID_CACHE[mkey] = m.to(cm.device)
+        parse = torch.einsum("ij,njhw->nihw", _GRID_CACHE[mkey], old_parse)
         g_in = torch.cat((batch["agnostic"], batch["densepose"], warped_cloth), 1)
     return g_in.detach(), parse.detach()
 
@@ -65,9 +75,33 @@ class Stage2Trainer:
         self.crit_gan = GANLoss("hinge")
         self.vgg_weights = [1.0 / 32, 1.0 / 16, 1.0 / 8, 1.0 / 4, 1.0]
         self.lambda_feat, self.lambda_vgg = lambda_feat, lambda_vgg
-        self.opt_g = torch.optim.Adam(generator.parameters(), lr=g_lr, betas=(0.0, 0.9), fused=True)
-        self.opt_d = torch.optim.Adam(discriminator.parameters(), lr=d_lr, betas=(0.0, 0.9), fused=True)
+        self.opt_g = torch.optim.Adam(generator.parameters(), lr=g_lr, betas=(0.0, 0.9), fused=True, capturable=True)
+        self.opt_d = torch.optim.Adam(discriminator.parameters(), lr=d_lr, betas=(0.0, 0.9), fused=True, capturable=True)
         self.reducers = reducers or {}  # {"G": GradBucketReducer, "D": ...} for data-parallel runs
+
+    def capture(self, batch, fine_h, fine_w, warm=2):
+        """Capture one whole step (both optimiser updates) into a CUDA graph over static copies of `batch`: removes the
+        ~5000 Python-driven launches per step from the critical path.  Returns self; call replay(new_batch)."""
+        self._static = {k: v.clone() for k, v in batch.items()}
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(warm):
+                self.step(self._static, fine_h, fine_w)
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._graph_out = self.step(self._static, fine_h, fine_w)
+        return self
+
+    def replay(self, batch=None):
+        if batch is not None:
+            for k, v in batch.items():
+                self._static[k].copy_(v, non_blocking=True)
+        self._graph.replay()
+        return self._graph_out
 
     @staticmethod
     def _split(pred):
@@ -127,4 +161,98 @@ def synthetic_batch(n, h, w, device, seed=0):
 
     b = {"cloth": smooth(3), "cloth_mask": (smooth(1) > 0).float(), "parse_agnostic": onehot(13), "densepose": smooth(3),
          "agnostic": smooth(3), "image": smooth(3)}
+    return {k: v.to(device) for k, v in b.items()}
+
+
+# ------------------------------------------------------------------------------------------------ stage 1 (train_condition.py)
+
+class Stage1Trainer:
+    """One train_condition.py step (train_condition.py:133-286) with the README's flags (--Ddownx2 --Ddropout --lasttvonly
+    --interflowloss --occlusion): tocg forward+backward on this repo's kernels (train-mode BatchNorm), L1 + VGG + TV + CE + LSGAN."""
+
+    def __init__(self, tocg, D, vgg, lr=2e-4, lasttvonly=True, interflowloss=True, occlusion=True, tvlambda=2.0, ce_lambda=10.0,
+                 gan_lambda=1.0, reducers=None):
+        self.tocg, self.D, self.vgg = tocg, D, vgg
+        self.lasttvonly, self.interflowloss, self.occlusion = lasttvonly, interflowloss, occlusion
+        self.tvlambda, self.ce_lambda, self.gan_lambda = tvlambda, ce_lambda, gan_lambda
+        self.vgg_weights = [1.0 / 32, 1.0 / 16, 1.0 / 8, 1.0 / 4, 1.0]
+        self.opt_g = torch.optim.Adam(tocg.parameters(), lr=lr, betas=(0.5, 0.999), fused=True, capturable=True)
+        self.opt_d = torch.optim.Adam(D.parameters(), lr=lr, betas=(0.5, 0.999), fused=True, capturable=True)
+        self.reducers = reducers or {}
+
+    @staticmethod
+    def _remove_overlap(seg_out, warped_cm):  # train_condition.py:26-31
+        return warped_cm - torch.cat([seg_out[:, 1:3], seg_out[:, 5:]], 1).sum(1, keepdim=True) * warped_cm
+
+    @staticmethod
+    def _lsgan(pred, real):  # networks.GANLoss (LSGAN) on the last output of every scale (networks.py:288-299)
+        return sum(F.mse_loss(p[-1].float(), torch.full_like(p[-1], 1.0 if real else 0.0, dtype=torch.float32)) for p in pred)
+
+    def step(self, batch):
+        from . import autograd_g, autograd_tocg
+        from .tocg import make_grid
+        c_paired, im_c, pcm = batch["cloth"], batch["parse_cloth"], batch["pcm"]
+        cm_paired = (batch["cloth_mask"] > 0.5).float()
+        input1 = torch.cat([c_paired, cm_paired], 1)
+        input2 = torch.cat([batch["parse_agnostic"], batch["densepose"]], 1)
+        flow_list, seg, warped_c, warped_cm = autograd_tocg.tocg_forward_train(self.tocg, input1, input2)
+        mask = torch.ones_like(seg.detach())
+        mask = torch.cat([mask[:, :3], warped_cm, mask[:, 4:]], 1)  # clothmask_composition == 'warp_grad'
+        seg = seg * mask
+        if self.occlusion:
+            warped_cm = self._remove_overlap(F.softmax(seg, dim=1), warped_cm)
+            warped_c = warped_c * warped_cm + (1 - warped_cm)
+        loss_l1 = F.l1_loss(warped_cm, pcm)
+        loss_vgg = autograd_g.vgg_loss(self.vgg, self.vgg_weights, warped_c, im_c)
+        loss_tv = 0
+        for flow in (flow_list[-1:] if self.lasttvonly else flow_list):
+            loss_tv = loss_tv + (flow[:, 1:] - flow[:, :-1]).abs().mean() + (flow[:, :, 1:] - flow[:, :, :-1]).abs().mean()
+        n, _, ih, iw = c_paired.shape
+        if self.interflowloss:
+            key = ("s1grid", n, ih, iw, str(c_paired.device))
+            if key not in _GRID_CACHE:
+                _GRID_CACHE[key] = make_grid(n, ih, iw).to(c_paired.device)
+            grid = _GRID_CACHE[key]
+            for i in range(len(flow_list) - 1):
+                fl = flow_list[i]
+                fh, fw = fl.shape[1], fl.shape[2]
+                fl = F.interpolate(fl.permute(0, 3, 1, 2), size=(ih, iw), mode="bilinear").permute(0, 2, 3, 1)
+                fn = torch.cat([fl[..., 0:1] / ((fw - 1.0) / 2.0), fl[..., 1:2] / ((fh - 1.0) / 2.0)], 3)
+                wc = F.grid_sample(c_paired, fn + grid, padding_mode="border", align_corners=False)
+                wcm = F.grid_sample(cm_paired, fn + grid, padding_mode="border", align_corners=False)
+                wcm = self._remove_overlap(F.softmax(seg, dim=1), wcm)
+                loss_l1 = loss_l1 + F.l1_loss(wcm, pcm) / (2 ** (4 - i))
+                loss_vgg = loss_vgg + autograd_g.vgg_loss(self.vgg, self.vgg_weights, wc, im_c) / (2 ** (4 - i))
+        ce = F.cross_entropy(seg, batch["parse_onehot"][:, 0].long(), ignore_index=250)  # utils.cross_entropy2d
+        soft = torch.softmax(seg, 1)
+        d_in = torch.cat((input1.detach(), input2.detach(), soft), 1)
+        loss_g_gan = self._lsgan(autograd_tocg.tocg_discriminator_forward_train(self.D, d_in), True)
+        pred_fake = autograd_tocg.tocg_discriminator_forward_train(self.D, d_in.detach())
+        pred_real = autograd_tocg.tocg_discriminator_forward_train(self.D, torch.cat((input1.detach(), input2.detach(), batch["parse"]), 1))
+        loss_d = self._lsgan(pred_fake, False) + self._lsgan(pred_real, True)
+        loss_g = (10 * loss_l1 + loss_vgg + self.tvlambda * loss_tv) + (ce * self.ce_lambda + loss_g_gan * self.gan_lambda)
+        self.opt_g.zero_grad(set_to_none=True)
+        self.opt_d.zero_grad(set_to_none=True)
+        loss_g.backward()
+        d_stale = [p.grad for p in self.D.parameters()]  # the G loss also back-propagates into D: the reference zeroes it (optimizer_D.zero_grad)
+        if "G" in self.reducers:
+            self.reducers["G"].reduce()
+        self.opt_g.step()
+        del d_stale
+        self.opt_d.zero_grad(set_to_none=True)
+        loss_d.backward()
+        if "D" in self.reducers:
+            self.reducers["D"].reduce()
+        self.opt_d.step()
+        return {"loss_g": loss_g.detach(), "loss_d": loss_d.detach(), "l1": loss_l1.detach(), "vgg": loss_vgg.detach(), "ce": ce.detach()}
+
+
+def synthetic_batch_stage1(n, h, w, device, seed=0):
+    b = synthetic_batch(n, h, w, "cpu", seed)
+    g = torch.Generator(device="cpu").manual_seed(seed + 1)
+    lab = torch.randint(0, 13, (n, h // 32, w // 32), generator=g).repeat_interleave(32, 1).repeat_interleave(32, 2)
+    b["parse_onehot"] = lab[:, None].float()
+    b["parse"] = torch.zeros(n, 13, h, w).scatter_(1, lab[:, None], 1.0)
+    b["pcm"] = (lab[:, None] == 3).float()
+    b["parse_cloth"] = b["image"] * b["pcm"] + (1 - b["pcm"])
     return {k: v.to(device) for k, v in b.items()}

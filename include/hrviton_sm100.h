@@ -96,14 +96,20 @@ int hrv_instnorm_stats(const hrv_tensor* x0, int32_t x0_shift, const hrv_tensor*
 int hrv_instnorm_apply(const hrv_tensor* x, const float* mean, const float* rstd, int32_t act,
                        const hrv_tensor* y, hrv_stream stream);
 
+/* y = act(((x - mean[n,c]) * rstd[n,c]) * gamma[c] + beta[c] + res): train-mode BatchNorm2d (mean/rstd = batch statistics
+ * replicated per image) + ReLU + residual of ResBlock (networks.py:188-198). gamma/beta/res optional. */
+int hrv_norm_apply_affine(const hrv_tensor* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                          const hrv_tensor* res, int32_t act, const hrv_tensor* y, hrv_stream stream);
+
 /* Backward of  h = act(xn*(1+gamma)+beta),  xn = InstanceNorm(cat(up2^x0_shift(x0), x1) + noise*noise_scale)
  * (network_generator.py:101-122,170-171), pass 1 of 2: per element dv = dh*act'(h), dgamma = dv*xn, dbeta = dv,
  * dxn = dv*(1+gamma); writes dgb (bf16 (n,h,w,2C), columns 2c = dgamma_c, 2c+1 = dbeta_c = dY of the gamma|beta GEMM; optional)
  * and dxn (bf16 (n,h,w,C)); accumulates sums[N][C][4] (fp64, zeroed by the call) = {sum dxn, sum dxn*xn, sum dgamma, sum dbeta}.
- * gamma == NULL means plain InstanceNorm + activation (the discriminators): dxn = dv. h is ignored when act == NONE. */
+ * gamma == NULL means plain Instance/BatchNorm + activation: dxn = dv * chan_scale[c] (chan_scale = the BatchNorm affine weight,
+ * NULL = 1). h is ignored when act == NONE. */
 int hrv_norm_bwd_reduce(const hrv_tensor* dh, const hrv_tensor* h, const hrv_tensor* gamma, const hrv_tensor* x0,
                         int32_t x0_shift, const hrv_tensor* x1, int32_t H, int32_t W, const float* noise,
-                        const float* noise_scale, const float* mean, const float* rstd, int32_t act,
+                        const float* noise_scale, const float* mean, const float* rstd, const float* chan_scale, int32_t act,
                         const hrv_tensor* dgb, const hrv_tensor* dxn, double* sums, hrv_stream stream);
 
 /* Pass 2: InstanceNorm backward dxs = rstd*(dxn - m1 - xn*m2) (m1 = sum dxn / HW, m2 = sum dxn*xn / HW, [N][C] fp32) for the

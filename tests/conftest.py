@@ -10,6 +10,10 @@ import hrv_loader  # noqa: E402
 
 hrv_loader.load()
 
+import torch  # noqa: E402
+
+torch.set_num_threads(min(16, os.cpu_count() or 1))  # the CPU oracle oversubscribes badly on 128-core hosts
+
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 

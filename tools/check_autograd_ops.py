@@ -47,3 +47,34 @@ for (h, w) in [(16, 12), (17, 13)]:
     y = y[:, :y_ref.shape[2], :y_ref.shape[3], :24].permute(0, 3, 1, 2).float()
     (y * R).sum().backward()
     print("s2d conv %dx%d: fwd %.2e dx %.2e dw %.2e" % (h, w, rel(y, y_ref), rel(x2.grad, x.grad), rel(w2.grad, wt.grad)))
+# ---- train-mode BatchNorm + ReLU (+ residual), c = 13 (padded) and 96
+from hrviton_b200 import autograd_tocg as at
+for c, with_res in [(96, True), (13, True), (96, False)]:
+    bn = torch.nn.BatchNorm2d(c).to(dev).train()
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5); bn.bias.normal_(0, 0.2)
+    x = torch.randn(2, c, 17, 13, device=dev).bfloat16().float().requires_grad_(True)
+    r = torch.randn(2, c, 17, 13, device=dev).bfloat16().float().requires_grad_(True)
+    y_ref = torch.relu(bn(x) + (r if with_res else 0)); R = torch.randn_like(y_ref); (y_ref * R).sum().backward()
+    gx, gr, gw, gb = x.grad.clone(), (r.grad.clone() if with_res else None), bn.weight.grad.clone(), bn.bias.grad.clone()
+    rm_ref = bn.running_mean.clone(); rv_ref = bn.running_var.clone()
+    bn2 = torch.nn.BatchNorm2d(c).to(dev).train()
+    with torch.no_grad():
+        bn2.weight.copy_(bn.weight); bn2.bias.copy_(bn.bias)
+    x2 = x.detach().clone().requires_grad_(True); r2 = r.detach().clone().requires_grad_(True)
+    y = at.BatchNormActFn.apply(ag.FromNCHW.apply(x2, None, None), bn2.weight, bn2.bias, ag.FromNCHW.apply(r2, None, None) if with_res else None, bn2, 1)
+    yn = y[..., :c].permute(0, 3, 1, 2).float(); (yn * R).sum().backward()
+    print("bn_train c=%d res=%s: fwd %.2e dx %.2e dres %s dw %.2e db %.2e  run_mean %.2e run_var %.2e" % (
+        c, with_res, rel(yn, y_ref), rel(x2.grad, gx), ("%.2e" % rel(r2.grad, gr)) if with_res else "-", rel(bn2.weight.grad, gw), rel(bn2.bias.grad, gb),
+        rel(bn2.running_mean, rm_ref), rel(bn2.running_var, rv_ref)))
+# ---- 3x3 stride-2 pad-1 conv through space-to-depth
+for (h, w) in [(16, 12), (17, 13)]:
+    x = torch.randn(2, 4, h, w, device=dev).bfloat16().float().requires_grad_(True)
+    wt = (torch.randn(24, 4, 3, 3, device=dev) * 0.1).bfloat16().float().requires_grad_(True)
+    y_ref = F.conv2d(x, wt, None, stride=2, padding=1); R = torch.randn_like(y_ref); (y_ref * R).sum().backward()
+    x2 = x.detach().clone().requires_grad_(True); w2 = wt.detach().clone().requires_grad_(True)
+    src = ag.space_to_depth_t(ag.FromNCHW.apply(x2, None, None))
+    y = ag.conv(src, ag._s2d_weight_t(w2), None, pad=1)
+    y = y[:, :y_ref.shape[2], :y_ref.shape[3], :24].permute(0, 3, 1, 2).float()
+    (y * R).sum().backward()
+    print("s2d conv k3s2p1 %dx%d: fwd %.2e dx %.2e dw %.2e" % (h, w, rel(y, y_ref), rel(x2.grad, x.grad), rel(w2.grad, wt.grad)))
