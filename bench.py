@@ -300,7 +300,9 @@ def main():
         h2d_bytes = int(sum(v.numel() * v.element_size() for v in batch_h.values()))
         d2h_bytes = 8
 
-        use_graph = not args.no_graph and not stage1
+        # multi-rank runs launch eagerly: capturing the NCCL gradient all-reduce inside the step graph hung on the 2-GPU box
+        # (profiles/README.md); the ~10% CPU launch overhead shows up in the N>1 numbers, not in N=1
+        use_graph = not args.no_graph and not stage1 and world == 1
         if use_graph:
             try:
                 trainer.step(batch_d, H, W)  # first eager step: lazy initialisation (optimizer state, func attributes, caches)
