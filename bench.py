@@ -214,7 +214,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: 4 for train_stage2, 8 for gen_fwd)")
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: 8 for train_stage2 and gen_fwd, 4 for train_stage1)")
     ap.add_argument("--workload", default="train_stage2", choices=["train_stage2", "train_stage1", "gen_fwd"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="train_stage2: launch eagerly instead of replaying a CUDA graph")
@@ -241,7 +241,7 @@ def main():
     K = args.steps
     train = args.workload in ("train_stage2", "train_stage1")
     stage1 = args.workload == "train_stage1"
-    B = args.batch or (4 if train else 8)
+    B = args.batch or (4 if stage1 else 8)
 
     def barrier():
         if world > 1:
@@ -283,7 +283,10 @@ def main():
                     return tr1.step(b)
 
                 def capture(self, b, h, w):
-                    raise RuntimeError("stage-1 step is launched eagerly (Dropout RNG + BatchNorm counters are not graph-captured yet)")
+                    tr1.capture(b)
+
+                def replay(self, b=None):
+                    return tr1.replay(b)
             trainer = _Shim()
             make_batch = train_step.synthetic_batch_stage1
         else:
@@ -302,7 +305,7 @@ def main():
 
         # multi-rank runs launch eagerly: capturing the NCCL gradient all-reduce inside the step graph hung on the 2-GPU box
         # (profiles/README.md); the ~10% CPU launch overhead shows up in the N>1 numbers, not in N=1
-        use_graph = not args.no_graph and not stage1 and world == 1
+        use_graph = not args.no_graph and world == 1
         if use_graph:
             try:
                 trainer.step(batch_d, H, W)  # first eager step: lazy initialisation (optimizer state, func attributes, caches)

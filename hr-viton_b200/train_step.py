@@ -65,7 +65,34 @@ def make_generator_inputs(tocg, batch, fine_h, fine_w, occlusion=False):
     return g_in.detach(), parse.detach()
 
 
-class Stage2Trainer:
+class _GraphMixin:
+    """Capture one whole step (all optimiser updates) into a CUDA graph over static copies of the batch: removes the thousands of
+    Python-driven launches per step from the critical path.  capture(batch, *step_args) once, then replay(new_batch)."""
+
+    def capture(self, batch, *step_args, warm=2):
+        self._static = {k: v.clone() for k, v in batch.items()}
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(warm):
+                self.step(self._static, *step_args)
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._graph_out = self.step(self._static, *step_args)
+        return self
+
+    def replay(self, batch=None):
+        if batch is not None:
+            for k, v in batch.items():
+                self._static[k].copy_(v, non_blocking=True)
+        self._graph.replay()
+        return self._graph_out
+
+
+class Stage2Trainer(_GraphMixin):
     """Holds the optimisers / criteria of train_generator.py:145-159 and runs one step."""
 
     def __init__(self, tocg, generator, discriminator, vgg, lambda_feat=10.0, lambda_vgg=10.0, g_lr=1e-4, d_lr=4e-4,
@@ -78,30 +105,6 @@ class Stage2Trainer:
         self.opt_g = torch.optim.Adam(generator.parameters(), lr=g_lr, betas=(0.0, 0.9), fused=True, capturable=True)
         self.opt_d = torch.optim.Adam(discriminator.parameters(), lr=d_lr, betas=(0.0, 0.9), fused=True, capturable=True)
         self.reducers = reducers or {}  # {"G": GradBucketReducer, "D": ...} for data-parallel runs
-
-    def capture(self, batch, fine_h, fine_w, warm=2):
-        """Capture one whole step (both optimiser updates) into a CUDA graph over static copies of `batch`: removes the
-        ~5000 Python-driven launches per step from the critical path.  Returns self; call replay(new_batch)."""
-        self._static = {k: v.clone() for k, v in batch.items()}
-        cur = torch.cuda.current_stream()
-        side = torch.cuda.Stream()
-        side.wait_stream(cur)
-        with torch.cuda.stream(side):
-            for _ in range(warm):
-                self.step(self._static, fine_h, fine_w)
-        cur.wait_stream(side)
-        torch.cuda.synchronize()
-        self._graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self._graph):
-            self._graph_out = self.step(self._static, fine_h, fine_w)
-        return self
-
-    def replay(self, batch=None):
-        if batch is not None:
-            for k, v in batch.items():
-                self._static[k].copy_(v, non_blocking=True)
-        self._graph.replay()
-        return self._graph_out
 
     @staticmethod
     def _split(pred):
@@ -166,7 +169,7 @@ def synthetic_batch(n, h, w, device, seed=0):
 
 # ------------------------------------------------------------------------------------------------ stage 1 (train_condition.py)
 
-class Stage1Trainer:
+class Stage1Trainer(_GraphMixin):
     """One train_condition.py step (train_condition.py:133-286) with the README's flags (--Ddownx2 --Ddropout --lasttvonly
     --interflowloss --occlusion): tocg forward+backward on this repo's kernels (train-mode BatchNorm), L1 + VGG + TV + CE + LSGAN."""
 

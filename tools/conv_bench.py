@@ -6,6 +6,7 @@ import hrv_loader; hrv_loader.load()
 from hrviton_b200 import ops
 from hrviton_b200.ops import Act
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 4
+REPS = int(sys.argv[2]) if len(sys.argv) > 2 else 10  # 1 => single launch per case (ncu captures)
 cases = [  # cin, cout(n_gemm), k, h, w, spade
     (128, 160, 3, 1024, 768, True), (128, 288, 3, 512, 384, True), (128, 544, 3, 256, 192, True), (128, 64, 3, 1024, 768, True),
     (80, 32, 3, 1024, 768, False), (80, 32, 1, 1024, 768, False), (32, 32, 3, 1024, 768, False), (144, 64, 3, 512, 384, False),
@@ -26,12 +27,26 @@ for cin, cout, k, h, w, spade in cases:
         pw = ops.pack_weight(wt, (k // 2, k // 2))
         out = Act.empty(B, h, w, cout)
         fn = lambda: ops.conv2d(x, pw, out)
-    for _ in range(3): fn()
+    for _ in range(3 if REPS > 1 else 0): fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(10): fn()
+    for _ in range(REPS): fn()
     e1.record(); torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 10
+    ms = e0.elapsed_time(e1) / REPS
     fl = 2.0 * cin * cout * k * k * B * h * w
     print("%4d->%4d k%d %4dx%-4d %s  %7.3f ms  %7.1f TFLOP/s" % (cin, cout, k, h, w, "spade " if spade else "linear", ms, fl / ms / 1e9), flush=True)
+
+# weight-gradient kernel on the same layer shapes
+for cin, cout, k, h, w in [(128, 160, 3, 1024, 768), (128, 288, 3, 512, 384), (80, 32, 3, 1024, 768), (1040, 512, 3, 64, 48), (256, 256, 3, 256, 192)]:
+    x = Act(torch.randn(B, h, w, ops.round_up(cin, 8), device="cuda").to(torch.bfloat16), c=cin)
+    dy = Act(torch.randn(B, h, w, ops.round_up(cout, 8), device="cuda").to(torch.bfloat16), c=cout)
+    fn = lambda: ops.conv2d_wgrad(x, dy, k, k, k // 2)
+    for _ in range(3 if REPS > 1 else 0): fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(REPS): fn()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / REPS
+    print("wgrad %4d->%4d k%d %4dx%-4d          %7.3f ms  %7.1f TFLOP/s" % (cin, cout, k, h, w, ms, 2.0 * cin * cout * k * k * B * h * w / ms / 1e9), flush=True)
