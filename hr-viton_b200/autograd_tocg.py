@@ -1,10 +1,9 @@
 """Training path (forward + backward) of the condition generator ("tocg") and the stage-1 discriminator.
 
 Convolutions (forward, dgrad, wgrad), train-mode BatchNorm (single-pass batch statistics + fused normalise/affine/ReLU/residual,
-fused backward), InstanceNorm and activations run on this repo's kernels through the autograd nodes of autograd_g.  The small
-resampling glue between them (bilinear x2 of feature maps and flows, grid_sample of the appearance-flow warp, channel concats) uses
-torch ops in this training path — their fused forward kernels (hrv_flow_warp, hrv_bilinear_up2_add, channel-slice buffers) serve the
-inference path; their backward kernels are the next step."""
+fused backward), InstanceNorm and activations run on this repo's kernels through the autograd nodes of autograd_g.  The resampling between them is on kernels too: bilinear x2 (+ lateral add) forward/backward (hrv_bilinear_up2_add / _bwd)
+and the fused appearance-flow warp forward/backward (hrv_flow_warp / hrv_flow_warp_bwd).  Only channel concatenations (torch.cat) and the
+dropout of the stage-1 discriminator remain torch ops in this training path."""
 import torch
 import torch.nn.functional as F
 
@@ -59,9 +58,48 @@ class BatchNormActFn(torch.autograd.Function):
         return dxb, dgamma[:c].contiguous(), dbeta[:c].contiguous(), dres, None, None
 
 
-def _up2(buf):
-    """Bilinear x2 (align_corners=False) of a pixel-major buffer, differentiable (torch op on the channels-last view)."""
-    return F.interpolate(buf.permute(0, 3, 1, 2), scale_factor=2, mode="bilinear", align_corners=False).permute(0, 2, 3, 1).contiguous()
+class Up2Fn(torch.autograd.Function):
+    """out = bilinear_up2(a) (+ b) on pixel-major bf16 buffers (F.interpolate(x2, bilinear) [+ lateral], networks.py:130,181):
+    hrv_bilinear_up2_add forward, hrv_bilinear_up2_bwd (adjoint gather) backward."""
+
+    @staticmethod
+    def forward(ctx, a_buf, b_buf):
+        a = Act(a_buf)
+        out = Act.empty(a.n, 2 * a.h, 2 * a.w, a.c, pitch=a_buf.shape[3])
+        ops.bilinear_up2_add(a, Act(b_buf) if b_buf is not None else None, out)
+        return out.buf
+
+    @staticmethod
+    def backward(ctx, dout):
+        dout = dout.contiguous()
+        da = ops.bilinear_up2_bwd(Act(dout)).buf if ctx.needs_input_grad[0] else None
+        return da, (dout if ctx.needs_input_grad[1] else None)
+
+
+def _up2(buf, add=None):
+    return Up2Fn.apply(buf, add)
+
+
+class FlowWarpFn(torch.autograd.Function):
+    """(warped, flow_up) = hrv_flow_warp(src, flow_lo) — flow x2 bilinear + normalise + base grid + grid_sample(border) in one kernel
+    (networks.py:133-135,147-152); backward = hrv_flow_warp_bwd (scatter-add d_src, analytic d_flow, adjoint of the flow up-sampling)."""
+
+    @staticmethod
+    def forward(ctx, src_buf, flow_lo):
+        src = Act(src_buf)
+        flow_lo = flow_lo.contiguous()
+        dst = Act.empty(src.n, src.h, src.w, src.c, pitch=src_buf.shape[3])
+        flow_up, _ = ops.flow_warp(flow_lo, src, dst)
+        ctx.save_for_backward(src_buf, flow_lo)
+        return dst.buf, flow_up
+
+    @staticmethod
+    def backward(ctx, d_dst, d_flow_up):
+        src_buf, flow_lo = ctx.saved_tensors
+        if d_dst is None:
+            d_dst = torch.zeros_like(src_buf)
+        dsrc, dflo = ops.flow_warp_bwd(flow_lo, Act(src_buf), Act(d_dst.contiguous()), d_flow_up, want_dsrc=ctx.needs_input_grad[0])
+        return (dsrc.buf if dsrc is not None else None), dflo
 
 
 def _resblock(rb, x_buf):
@@ -76,7 +114,7 @@ def _resblock(rb, x_buf):
     elif rb.kind == "same":
         r = conv(x_buf, rb.scale.weight, rb.scale.bias, pad=0)
     else:
-        r = _up2(conv(x_buf, rb.scale[1].weight, rb.scale[1].bias, pad=0))  # 1x1 commuted below the up-sampling
+        r = _up2(conv(x_buf, rb.scale[1].weight, rb.scale[1].bias, pad=0))  # 1x1 commuted below the up-sampling (kernel fwd + bwd)
     bn0, bn1 = rb.block[1], rb.block[4]
     h = BatchNormActFn.apply(conv(r, rb.block[0].weight, rb.block[0].bias), bn0.weight, bn0.bias, None, bn0, ACT_RELU)
     return BatchNormActFn.apply(conv(h, rb.block[3].weight, rb.block[3].bias), bn1.weight, bn1.bias, r, bn1, ACT_RELU)
@@ -107,7 +145,7 @@ def tocg_forward_train(m, input1, input2):
     ngf = m.ngf
     a = FromNCHW.apply(input1.float(), None, None)
     b = FromNCHW.apply(input2.float(), None, None)
-    a2 = b
+    a1, a2 = a, b
     e1, e2 = [], []
     for k in range(5):
         a = _resblock(m.ClothEncoder[k], a)
@@ -122,18 +160,19 @@ def tocg_forward_train(m, input1, input2):
     t1 = e1[4]
     for i in range(1, 5):
         lvl = 4 - i
-        t1 = _up2(t1) + conv(e1[lvl], m.conv1[lvl].weight, m.conv1[lvl].bias, pad=0)
-        warped, flow_up = _warp(t1.permute(0, 3, 1, 2).float(), flows[-1])
-        warped = warped.permute(0, 2, 3, 1).to(torch.bfloat16).contiguous()
+        t1 = _up2(t1, conv(e1[lvl], m.conv1[lvl].weight, m.conv1[lvl].bias, pad=0))
+        warped, flow_up = FlowWarpFn.apply(t1, flows[-1])
         bt = m.bottleneck[i - 1][0]
         bott = conv(x, bt.weight, bt.bias, act=ACT_RELU)
         flow = flow_up + conv(torch.cat([warped, bott], 3), fc[i].weight, fc[i].bias, out_f32_nhwc=True)
         flows.append(flow)
         x = _resblock(m.SegDecoder[i], torch.cat([x, e2[lvl], warped], 3))
-    warped_in, _ = _warp(input1.float(), flows[-1])
-    fin = torch.cat([x, a2, FromNCHW.apply(warped_in, None, None)], 3)
+    warped_in_buf, _ = FlowWarpFn.apply(a1, flows[-1])
+    fin = torch.cat([x, a2, warped_in_buf], 3)
     seg_buf = _resblock(m.out_layer, fin)
     seg = seg_buf[..., :m.io[2]].permute(0, 3, 1, 2).float()
+    c1 = m.io[0]
+    warped_in = warped_in_buf[..., :c1].permute(0, 3, 1, 2).float()
     return flows, seg, warped_in[:, :-1], warped_in[:, -1:]
 
 

@@ -12,7 +12,7 @@ NHWC, NCHW = 0, 1
 EPI_LINEAR, EPI_SPADE = 0, 1
 
 EXPORTS = ["hrv_conv2d_fwd", "hrv_instnorm_stats", "hrv_instnorm_apply", "hrv_norm_apply_affine", "hrv_norm_bwd_reduce", "hrv_norm_bwd_apply", "hrv_act_bwd_bias", "hrv_conv2d_wgrad", "hrv_nchw_to_nhwc", "hrv_nhwc_to_nchw",
-           "hrv_space_to_depth", "hrv_avgpool3s2", "hrv_bilinear_up2_add", "hrv_flow_warp", "hrv_last_error",
+           "hrv_space_to_depth", "hrv_avgpool3s2", "hrv_bilinear_up2_add", "hrv_flow_warp", "hrv_bilinear_up2_bwd", "hrv_flow_warp_bwd", "hrv_last_error",
            "hrv_version", "hrv_device_sm_count"]
 
 
@@ -59,6 +59,8 @@ def lib():
     L.hrv_avgpool3s2.argtypes = [TP, TP, vp]
     L.hrv_bilinear_up2_add.argtypes = [TP, TP, TP, vp]
     L.hrv_flow_warp.argtypes = [vp, vp, vp, TP, TP, vp, vp, vp]
+    L.hrv_bilinear_up2_bwd.argtypes = [TP, TP, vp]
+    L.hrv_flow_warp_bwd.argtypes = [vp, vp, vp, TP, TP, vp, vp, vp, vp]
     for name in EXPORTS:
         fn = getattr(L, name)
         if name != "hrv_last_error":

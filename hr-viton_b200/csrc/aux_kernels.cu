@@ -498,3 +498,180 @@ extern "C" int hrv_flow_warp(const float* flow_lo, const float* lin_x, const flo
   flow_warp_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(flow_lo, lin_x, lin_y, mk(src), mk(dst), flow_up, idx_out, sx, sy, G, total);
   return launch_ok("flow_warp");
 }
+
+// ------------------------------------------------------------------------------------------------ backward of the resampling ops
+namespace hrv {
+
+// Adjoint of F.interpolate(bilinear, x2, align_corners=False) along one axis: low-res index i receives from high-res
+// d in {2i-1, 2i, 2i+1, 2i+2} with weights {0.25, 0.75, 0.75, 0.25}; the clamped border taps fold onto i (weights 1.0).
+__device__ __forceinline__ void up2_adj(int i, int n, float (&wt)[4]) {
+  wt[0] = i >= 1 ? 0.25f : 0.f;
+  wt[1] = i == 0 ? 1.0f : 0.75f;
+  wt[2] = i == n - 1 ? 1.0f : 0.75f;
+  wt[3] = i <= n - 2 ? 0.25f : 0.f;
+}
+
+// thread = (low-res pixel, 8-channel group): da[n,y,x,:] = sum over the 4x4 high-res neighbourhood of wy*wx*dout
+__global__ void bilinear_up2_bwd_kernel(View dout, View da, int G, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int g = (int)(idx % G);
+  const long long pix = idx / G;
+  const int x = (int)(pix % da.w);
+  const int y = (int)((pix / da.w) % da.h);
+  const int n = (int)(pix / ((long long)da.w * da.h));
+  float wy[4], wx[4], acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  up2_adj(y, da.h, wy);
+  up2_adj(x, da.w, wx);
+  const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(dout.ptr) + (long long)n * dout.h * dout.w * dout.pitch + g * 8;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int Y = 2 * y - 1 + j;
+    if (wy[j] == 0.f || Y < 0 || Y >= dout.h) continue;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int X = 2 * x - 1 + i;
+      if (wx[i] == 0.f || X < 0 || X >= dout.w) continue;
+      float f[8];
+      unpack8(ldg16(base + ((long long)Y * dout.w + X) * dout.pitch), f);
+      const float w = wy[j] * wx[i];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] = fmaf(w, f[k], acc[k]);
+    }
+  }
+  *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(da.ptr)) + pix * da.pitch + g * 8) = pack8(acc);
+}
+
+// Backward of flow_warp_kernel.  thread = (dst pixel, 8-channel group): recomputes the sampling coordinates exactly as the
+// forward, scatter-adds d_dst * w into d_src (fp32 accumulation buffer, atomics: the gather is irregular) and accumulates the
+// analytic coordinate gradient (grid_sample border semantics: zero where the coordinate was clamped) into d_flow_up (fp32).
+__global__ void flow_warp_bwd_kernel(const float* __restrict__ flow_lo, const float* __restrict__ lin_x, const float* __restrict__ lin_y,
+                                     View src, View ddst, float* __restrict__ dsrc32, float* __restrict__ dflow_up, float sx, float sy,
+                                     int G, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int g = (int)(idx % G);
+  const long long pix = idx / G;
+  const int W = ddst.w, H = ddst.h;
+  const int x = (int)(pix % W);
+  const int y = (int)((pix / W) % H);
+  const int n = (int)(pix / ((long long)W * H));
+  const int hl = H >> 1, wl = W >> 1;
+  int xa, xb, ya, yb;
+  float wxa, wxb, wya, wyb;
+  up2_taps(x, wl, xa, xb, wxa, wxb);
+  up2_taps(y, hl, ya, yb, wya, wyb);
+  const float2* fl = reinterpret_cast<const float2*>(flow_lo) + (long long)n * hl * wl;
+  const float2 f00 = __ldg(fl + (long long)ya * wl + xa), f01 = __ldg(fl + (long long)ya * wl + xb);
+  const float2 f10 = __ldg(fl + (long long)yb * wl + xa), f11 = __ldg(fl + (long long)yb * wl + xb);
+  const float fx = __fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(f00.x, wxa), __fmul_rn(f01.x, wxb)), wya), __fmul_rn(__fadd_rn(__fmul_rn(f10.x, wxa), __fmul_rn(f11.x, wxb)), wyb));
+  const float fy = __fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(f00.y, wxa), __fmul_rn(f01.y, wxb)), wya), __fmul_rn(__fadd_rn(__fmul_rn(f10.y, wxa), __fmul_rn(f11.y, wxb)), wyb));
+  const float gx = __fadd_rn(__fdiv_rn(fx, sx), __ldg(lin_x + x));
+  const float gy = __fadd_rn(__fdiv_rn(fy, sy), __ldg(lin_y + y));
+  const float ixr = __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(gx, 1.f), (float)src.w), 1.f), 2.f);
+  const float iyr = __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(gy, 1.f), (float)src.h), 1.f), 2.f);
+  const float ix = fminf(fmaxf(ixr, 0.f), (float)(src.w - 1)), iy = fminf(fmaxf(iyr, 0.f), (float)(src.h - 1));
+  const float mx = (ixr < 0.f || ixr > (float)(src.w - 1)) ? 0.f : 1.f;  // clip_coordinates_set_grad
+  const float my = (iyr < 0.f || iyr > (float)(src.h - 1)) ? 0.f : 1.f;
+  const float fx0 = floorf(ix), fy0 = floorf(iy);
+  const int x0 = (int)fx0, y0 = (int)fy0;
+  const float tx = ix - fx0, ty = iy - fy0;
+  const bool vx = x0 + 1 <= src.w - 1, vy = y0 + 1 <= src.h - 1;
+  const int x1 = vx ? x0 + 1 : x0, y1 = vy ? y0 + 1 : y0;
+  const float wx1 = vx ? tx : 0.f, wy1 = vy ? ty : 0.f, wx0 = 1.f - tx, wy0 = 1.f - ty;
+  if (g * 8 >= ((src.c + 7) & ~7)) return;
+  float d[8], a[8], b[8], c[8], e[8];
+  unpack8(ldg16(reinterpret_cast<const __nv_bfloat16*>(ddst.ptr) + pix * ddst.pitch + g * 8), d);
+  const long long ib = (long long)n * src.h * src.w;
+  const __nv_bfloat16* sp = reinterpret_cast<const __nv_bfloat16*>(src.ptr) + g * 8;
+  unpack8(ldg16(sp + (ib + (long long)y0 * src.w + x0) * src.pitch), a);
+  unpack8(ldg16(sp + (ib + (long long)y0 * src.w + x1) * src.pitch), b);
+  unpack8(ldg16(sp + (ib + (long long)y1 * src.w + x0) * src.pitch), c);
+  unpack8(ldg16(sp + (ib + (long long)y1 * src.w + x1) * src.pitch), e);
+  float dix = 0.f, diy = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    // value = a*wy0*wx0 + b*wy0*wx1 + c*wy1*wx0 + e*wy1*wx1 ; taps outside the image carry zero weight AND zero derivative
+    const float bb = vx ? b[k] : 0.f, cc = vy ? c[k] : 0.f, ee = (vx && vy) ? e[k] : 0.f;
+    dix += d[k] * ((bb - a[k]) * wy0 + (ee - cc) * (vy ? ty : 0.f));
+    diy += d[k] * ((cc - a[k]) * wx0 + (ee - bb) * (vx ? tx : 0.f));
+  }
+  if (dflow_up) {
+    // d ix / d gx = src.w/2 ; d gx / d flow_up.x = 1/sx
+    atomicAdd(dflow_up + pix * 2, dix * mx * (0.5f * (float)src.w) / sx);
+    atomicAdd(dflow_up + pix * 2 + 1, diy * my * (0.5f * (float)src.h) / sy);
+  }
+  if (dsrc32) {
+    const int cs = (src.c + 7) & ~7;
+    float* o00 = dsrc32 + (ib + (long long)y0 * src.w + x0) * cs + g * 8;
+    float* o01 = dsrc32 + (ib + (long long)y0 * src.w + x1) * cs + g * 8;
+    float* o10 = dsrc32 + (ib + (long long)y1 * src.w + x0) * cs + g * 8;
+    float* o11 = dsrc32 + (ib + (long long)y1 * src.w + x1) * cs + g * 8;
+    const float w00 = wy0 * wx0, w01 = wy0 * wx1, w10 = wy1 * wx0, w11 = wy1 * wx1;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      atomicAdd(o00 + k, d[k] * w00);
+      if (w01 != 0.f) atomicAdd(o01 + k, d[k] * w01);
+      if (w10 != 0.f) atomicAdd(o10 + k, d[k] * w10);
+      if (w11 != 0.f) atomicAdd(o11 + k, d[k] * w11);
+    }
+  }
+}
+
+// d_flow_lo[n,y,x,:] = adjoint of the x2 bilinear up-sampling applied to d_flow_up (2 fp32 channels)
+__global__ void flow_up2_bwd_kernel(const float* __restrict__ dup, float* __restrict__ dlo, int N, int hl, int wl) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)N * hl * wl;
+  if (idx >= total) return;
+  const int x = (int)(idx % wl), y = (int)((idx / wl) % hl), n = (int)(idx / ((long long)wl * hl));
+  float wy[4], wx[4], ax = 0.f, ay = 0.f;
+  up2_adj(y, hl, wy);
+  up2_adj(x, wl, wx);
+  const int H = 2 * hl, W = 2 * wl;
+  const float2* src = reinterpret_cast<const float2*>(dup) + (long long)n * H * W;
+  for (int j = 0; j < 4; ++j) {
+    const int Y = 2 * y - 1 + j;
+    if (wy[j] == 0.f || Y < 0 || Y >= H) continue;
+    for (int i = 0; i < 4; ++i) {
+      const int X = 2 * x - 1 + i;
+      if (wx[i] == 0.f || X < 0 || X >= W) continue;
+      const float2 v = __ldg(src + (long long)Y * W + X);
+      ax = fmaf(wy[j] * wx[i], v.x, ax);
+      ay = fmaf(wy[j] * wx[i], v.y, ay);
+    }
+  }
+  reinterpret_cast<float2*>(dlo)[idx] = make_float2(ax, ay);
+}
+
+}  // namespace hrv
+
+extern "C" int hrv_bilinear_up2_bwd(const hrv_tensor* dout, const hrv_tensor* da, hrv_stream stream) {
+  int rc;
+  if ((rc = check_bf16_vec(dout, "up2_bwd dout")) || (rc = check_bf16_vec(da, "up2_bwd da"))) return rc;
+  if (dout->h != 2 * da->h || dout->w != 2 * da->w) return set_error(HRV_EINVAL, "up2_bwd: dout must be 2x da");
+  const int G = (da->c + 7) / 8;
+  const long long total = (long long)da->n * da->h * da->w * G;
+  bilinear_up2_bwd_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(mk(dout), mk(da), G, total);
+  return launch_ok("bilinear_up2_bwd");
+}
+
+extern "C" int hrv_flow_warp_bwd(const float* flow_lo, const float* lin_x, const float* lin_y, const hrv_tensor* src, const hrv_tensor* ddst,
+                                 float* dsrc32, float* dflow_up, float* dflow_lo, hrv_stream stream) {
+  int rc;
+  if (!flow_lo || !lin_x || !lin_y) return set_error(HRV_EINVAL, "flow_warp_bwd: null argument");
+  if ((rc = check_bf16_vec(src, "flow_warp_bwd src")) || (rc = check_bf16_vec(ddst, "flow_warp_bwd ddst"))) return rc;
+  if ((ddst->h & 1) || (ddst->w & 1) || src->n != ddst->n || src->c != ddst->c) return set_error(HRV_EINVAL, "flow_warp_bwd: shape mismatch");
+  if (dflow_lo && !dflow_up) return set_error(HRV_EINVAL, "flow_warp_bwd: dflow_lo needs the dflow_up scratch buffer");
+  const int G = (src->c + 7) / 8;
+  const long long total = (long long)ddst->n * ddst->h * ddst->w * G;
+  const float sx = (float)((ddst->w / 2.0 - 1.0) / 2.0), sy = (float)((ddst->h / 2.0 - 1.0) / 2.0);
+  cudaStream_t st = (cudaStream_t)stream;
+  flow_warp_bwd_kernel<<<blocks_for(total, 256), 256, 0, st>>>(flow_lo, lin_x, lin_y, mk(src), mk(ddst), dsrc32, dflow_up, sx, sy, G, total);
+  if ((rc = launch_ok("flow_warp_bwd"))) return rc;
+  if (dflow_lo) {
+    const long long tl = (long long)ddst->n * (ddst->h / 2) * (ddst->w / 2);
+    flow_up2_bwd_kernel<<<blocks_for(tl, 256), 256, 0, st>>>(dflow_up, dflow_lo, ddst->n, ddst->h / 2, ddst->w / 2);
+    return launch_ok("flow_up2_bwd");
+  }
+  return HRV_OK;
+}

@@ -418,3 +418,29 @@ def norm_apply_affine(x, mean_nc, rstd_nc, gamma, beta, res, act, out=None):
         capi.check(capi.lib().hrv_norm_apply_affine(ctypes.byref(tx), mean_nc.data_ptr(), rstd_nc.data_ptr(), _p(gamma), _p(beta),
                                                     ctypes.byref(tr), act, ctypes.byref(ty), _stream()), "norm_apply_affine")
     return out
+
+
+def bilinear_up2_bwd(dout):
+    da = Act.empty(dout.n, dout.h // 2, dout.w // 2, dout.c)
+    td, ta = dout.ct(), da.ct()
+    with _Timed("up2_bwd", dout.n * dout.h * dout.w * dout.c * 2.0 * 1.25):
+        capi.check(capi.lib().hrv_bilinear_up2_bwd(ctypes.byref(td), ctypes.byref(ta), _stream()), "bilinear_up2_bwd")
+    return da
+
+
+def flow_warp_bwd(flow_lo, src, ddst, dflow_up_in, want_dsrc=True):
+    """Returns (dsrc bf16 Act | None, dflow_lo fp32 (N,h,w,2))."""
+    n, hl, wl, _ = flow_lo.shape
+    H, W = 2 * hl, 2 * wl
+    dev = flow_lo.device
+    c8 = round_up(src.c, 8)
+    dsrc32 = torch.zeros((n, src.h, src.w, c8), dtype=torch.float32, device=dev) if want_dsrc else None
+    dfu = dflow_up_in.float().contiguous().clone() if dflow_up_in is not None else torch.zeros((n, H, W, 2), dtype=torch.float32, device=dev)
+    dflo = torch.empty((n, hl, wl, 2), dtype=torch.float32, device=dev)
+    ts, td = src.ct(), ddst.ct()
+    with _Timed("flow_warp_bwd", n * H * W * src.c * 2.0 * 3, launches=2):
+        capi.check(capi.lib().hrv_flow_warp_bwd(flow_lo.data_ptr(), linspace_table(W, dev).data_ptr(), linspace_table(H, dev).data_ptr(),
+                                                ctypes.byref(ts), ctypes.byref(td), _p(dsrc32), dfu.data_ptr(), dflo.data_ptr(), _stream()),
+                   "flow_warp_bwd")
+    dsrc = Act(dsrc32.to(torch.bfloat16)) if want_dsrc else None
+    return dsrc, dflo

@@ -163,6 +163,18 @@ int hrv_bilinear_up2_add(const hrv_tensor* a, const hrv_tensor* b, const hrv_ten
 int hrv_flow_warp(const float* flow_lo, const float* lin_x, const float* lin_y, const hrv_tensor* src,
                   const hrv_tensor* dst, float* flow_up, int32_t* idx_out, hrv_stream stream);
 
+/* Backward of hrv_bilinear_up2_add w.r.t. `a`: da = adjoint of the x2 bilinear up-sampling applied to dout (bf16 NHWC;
+ * the gradient w.r.t. `b` is dout itself). */
+int hrv_bilinear_up2_bwd(const hrv_tensor* dout, const hrv_tensor* da, hrv_stream stream);
+
+/* Backward of hrv_flow_warp (F.grid_sample backward with border padding, networks.py:135,152, fused with the flow chain):
+ *   dsrc32 [n][H][W][roundup8(c)] fp32, caller-zeroed: += d_dst * lerp weight at the 4 taps (atomic scatter; may be NULL);
+ *   dflow_up [n][H][W][2] fp32, caller-initialised (zeros, or the gradient arriving directly at the up-sampled flow):
+ *            += analytic d/d(flow_up) of the sampled values (zero where the coordinate was clamped);
+ *   dflow_lo [n][H/2][W/2][2] fp32: written = adjoint of the x2 bilinear flow up-sampling applied to dflow_up (may be NULL). */
+int hrv_flow_warp_bwd(const float* flow_lo, const float* lin_x, const float* lin_y, const hrv_tensor* src, const hrv_tensor* ddst,
+                      float* dsrc32, float* dflow_up, float* dflow_lo, hrv_stream stream);
+
 /* Library / device introspection. */
 const char* hrv_last_error(void);
 int hrv_version(void);

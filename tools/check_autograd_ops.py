@@ -78,3 +78,20 @@ for (h, w) in [(16, 12), (17, 13)]:
     y = y[:, :y_ref.shape[2], :y_ref.shape[3], :24].permute(0, 3, 1, 2).float()
     (y * R).sum().backward()
     print("s2d conv k3s2p1 %dx%d: fwd %.2e dx %.2e dw %.2e" % (h, w, rel(y, y_ref), rel(x2.grad, x.grad), rel(w2.grad, wt.grad)))
+# ---- bilinear x2 (+add) and the fused flow warp: kernel forward/backward vs torch autograd
+a = torch.randn(2, 24, 9, 7, device=dev).bfloat16().float().requires_grad_(True)
+b = torch.randn(2, 24, 18, 14, device=dev).bfloat16().float().requires_grad_(True)
+y_ref = F.interpolate(a, scale_factor=2, mode="bilinear", align_corners=False) + b; R = torch.randn_like(y_ref); (y_ref * R).sum().backward()
+a2 = a.detach().clone().requires_grad_(True); b2 = b.detach().clone().requires_grad_(True)
+y = at.Up2Fn.apply(ag.FromNCHW.apply(a2, None, None), ag.FromNCHW.apply(b2, None, None)); yn = y.permute(0, 3, 1, 2).float(); (yn * R).sum().backward()
+print("up2_add: fwd %.2e da %.2e db %.2e" % (rel(yn, y_ref), rel(a2.grad, a.grad), rel(b2.grad, b.grad)))
+for c in (48, 4):
+    src = torch.randn(2, c, 32, 24, device=dev).bfloat16().float().requires_grad_(True)
+    flow = (torch.randn(2, 16, 12, 2, device=dev) * 2.5).requires_grad_(True)
+    w_ref, fu_ref = at._warp(src, flow); R = torch.randn_like(w_ref); R2 = torch.randn_like(fu_ref)
+    ((w_ref * R).sum() + (fu_ref * R2).sum()).backward()
+    s2 = src.detach().clone().requires_grad_(True); f2 = flow.detach().clone().requires_grad_(True)
+    wb, fu = at.FlowWarpFn.apply(ag.FromNCHW.apply(s2, None, None), f2)
+    wn = wb[..., :c].permute(0, 3, 1, 2).float()
+    ((wn * R).sum() + (fu * R2).sum()).backward()
+    print("flow_warp c=%d: fwd %.2e flow_up %.2e dsrc %.2e dflow %.2e" % (c, rel(wn, w_ref), rel(fu, fu_ref), rel(s2.grad, src.grad), rel(f2.grad, flow.grad)))
