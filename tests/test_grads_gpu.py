@@ -237,3 +237,80 @@ def test_stage1_train_step_runs():
     assert float((tocg.flow_conv[4].weight.detach() - w_before).abs().max()) > 0
     assert float((D.layer0[0].weight.detach() - d_before).abs().max()) > 0
     assert tocg.conv2[0].weight.grad is None  # dead branch of the reference (networks.py:131) receives no gradient
+
+
+def test_stage2_losses_match_oracle_pipeline():
+    """The measured workload itself: generator-update losses of Stage2Trainer (tocg -> glue -> G -> D -> hinge/feature-matching/VGG)
+    against the same pipeline evaluated with the CPU oracle networks (fp32) on identical weights, batch and SPADE noise."""
+    import types
+
+    import network_generator
+    import networks
+    import torch.nn.functional as F
+    from hrviton_b200 import autograd_g, train_step
+    os.environ["HRV_VGG_RANDOM_INIT"] = "1"
+    h = w = 256
+    n = 1
+    seed = 17
+    topt = types.SimpleNamespace(warp_feature="T1", out_layer="relu", cuda=True)
+    tocg = networks.ConditionGenerator(topt, 4, 16, 13, ngf=96, norm_layer=torch.nn.BatchNorm2d)
+    sdt = tocg.state_dict(); synth.fill_state_dict(sdt, seed); tocg.load_state_dict(sdt)
+    G = network_generator.SPADEGenerator(gen_opt(h, w, True), 9)
+    sdg = G.state_dict(); synth.fill_state_dict(sdg, seed + 1); G.load_state_dict(sdg)
+    D = network_generator.MultiscaleDiscriminator(gen_opt(h, w, True))
+    sdd = D.state_dict(); synth.fill_state_dict(sdd, seed + 2); D.load_state_dict(sdd)
+    torch.manual_seed(0)
+    vgg = networks.Vgg19()
+    vgg_cpu_sd = {k: v.clone() for k, v in vgg.state_dict().items()}
+    tocg, G, D, vgg = tocg.cuda().eval(), G.cuda().eval(), D.cuda().eval(), vgg.cuda().eval()
+    batch = train_step.synthetic_batch(n, h, w, "cpu", seed=seed)
+    cnt = [0]
+
+    def noise_dev(b, hh, ww):
+        t = synth.spade_noise(b, hh, ww, seed, cnt[0]).cuda()
+        cnt[0] += 1
+        return t
+
+    G.noise_source = noise_dev
+    # ---- product path (forward part of Stage2Trainer.step, generator update)
+    bd = {k: v.cuda() for k, v in batch.items()}
+    with torch.no_grad():
+        g_in, parse = train_step.make_generator_inputs(tocg, bd, h, w)
+        out = G(g_in, parse)
+        d_in = torch.cat((torch.cat((parse, out), 1), torch.cat((parse, bd["image"]), 1)), 0)
+        pred = autograd_g.discriminator_forward_train(D, d_in, need_wgrad=False, as_float=True)
+        fake = [[t[:n] for t in p] for p in pred]
+        real = [[t[n:] for t in p] for p in pred]
+        crit = network_generator.GANLoss("hinge")
+        gan = float(crit(fake, True, for_discriminator=False))
+        feat = float(sum(F.l1_loss(fake[i][j], real[i][j]) * 10.0 / 2 for i in range(2) for j in range(len(fake[i]) - 1)))
+        vl = float(autograd_g.vgg_loss(vgg, [1.0 / 32, 1.0 / 16, 1.0 / 8, 1.0 / 4, 1.0], out, bd["image"]))
+    # ---- oracle pipeline on the CPU (same glue code, oracle networks)
+    class _OracleTocg:
+        def __call__(self, i1, i2):
+            return orc.tocg_forward(sdt, i1, i2)
+    c2 = [0]
+
+    def noise_cpu(b, hh, ww):
+        t = synth.spade_noise(b, hh, ww, seed, c2[0])
+        c2[0] += 1
+        return t
+
+    with torch.no_grad():
+        g_in_r, parse_r = train_step.make_generator_inputs(_OracleTocg(), batch, h, w)
+        out_r = orc.spade_generator_forward(sdg, g_in_r, parse_r, noise_cpu)
+        pred_r = orc.gen_d_forward(sdd, torch.cat((torch.cat((parse_r, out_r), 1), torch.cat((parse_r, batch["image"]), 1)), 0))
+        fake_r = [[t[:n] for t in p] for p in pred_r]
+        real_r = [[t[n:] for t in p] for p in pred_r]
+        gan_r = float(crit(fake_r, True, for_discriminator=False))
+        feat_r = float(sum(F.l1_loss(fake_r[i][j], real_r[i][j]) * 10.0 / 2 for i in range(2) for j in range(len(fake_r[i]) - 1)))
+        vgg_cpu = networks.Vgg19()
+        vgg_cpu.load_state_dict(vgg_cpu_sd)
+        fx, fy = vgg_cpu(out_r), vgg_cpu(batch["image"])
+        vl_r = float(sum(wt * F.l1_loss(a, b) for wt, a, b in zip([1.0 / 32, 1.0 / 16, 1.0 / 8, 1.0 / 4, 1.0], fx, fy)))
+    print("STEP2LOSS parse agreement %.4f  image mean|d| %.3e" % (float((parse.cpu() == parse_r).float().mean()), float((out.cpu() - out_r).abs().mean())))
+    print("STEP2LOSS gan %.4f vs %.4f | feat %.4f vs %.4f | vgg %.4f vs %.4f" % (gan, gan_r, feat, feat_r, vl, vl_r))
+    assert float((parse.cpu() == parse_r).float().mean()) > 0.99  # argmax of blurred logits: a few pixels may flip under bf16
+    assert abs(gan - gan_r) < 0.05 + 0.05 * abs(gan_r)
+    assert abs(feat - feat_r) < 0.05 * abs(feat_r) + 0.02
+    assert abs(vl - vl_r) < 0.05 * abs(vl_r) + 0.01
