@@ -52,10 +52,13 @@ class ConvFn(torch.autograd.Function):
     need_wgrad=False skips dW (frozen nets: VGG, D inside the G step)."""
 
     @staticmethod
-    def forward(ctx, x_buf, w, bias, res_buf, act, out_fp32_nchw, pad, out_f32_nhwc):
+    def forward(ctx, x_buf, w, bias, res_buf, act, out_fp32_nchw, pad, out_f32_nhwc, out_hw=None):
         cout, cin, kh, kw = w.shape
         n, h, wd, _ = x_buf.shape
         oh, ow = h + 2 * pad - kh + 1, wd + 2 * pad - kw + 1
+        if out_hw is not None:  # cropped output (top-left aligned): rows/columns beyond it are never computed
+            assert out_hw[0] <= oh and out_hw[1] <= ow
+            oh, ow = out_hw
         xa = Act(x_buf, c=cin)
         pw = ops.pack_weight(w.detach(), (pad, pad))
         b = bias.detach().float().contiguous() if bias is not None else None
@@ -99,8 +102,7 @@ class ConvFn(torch.autograd.Function):
         n, h, wd, _ = x_buf.shape
         dx = dw = dres = None
         if ctx.needs_input_grad[0]:
-            wt = w.detach().flip(2, 3).transpose(0, 1).contiguous()  # (cin, cout, kh, kw)
-            pw = ops.pack_weight(wt, (kh - 1 - pad, kw - 1 - pad))
+            pw = ops.pack_weight(w, (kh - 1 - pad, kw - 1 - pad), dgrad=True)  # flipped/transposed operand, packed in one kernel
             dxa = Act.empty(n, h, wd, cin, pitch=x_buf.shape[3], zero=x_buf.shape[3] > ops.round_up(cin, 8))
             ops.conv2d(Act(dv_buf, c=cout), pw, dxa)
             dx = dxa.buf
@@ -108,12 +110,12 @@ class ConvFn(torch.autograd.Function):
             dw = _wgrad(x_buf, cin, dv_buf, cout, kh, kw, pad)
         if has_res and ctx.needs_input_grad[3]:
             dres = dv_buf
-        return dx, dw, db, dres, None, None, None, None
+        return dx, dw, db, dres, None, None, None, None, None
 
 
-def conv(x_buf, w, bias=None, res_buf=None, act=ACT_NONE, out_fp32_nchw=False, pad=None, out_f32_nhwc=False):
+def conv(x_buf, w, bias=None, res_buf=None, act=ACT_NONE, out_fp32_nchw=False, pad=None, out_f32_nhwc=False, out_hw=None):
     pad = w.shape[2] // 2 if pad is None else pad
-    return ConvFn.apply(x_buf, w, bias, res_buf, act, out_fp32_nchw, pad, out_f32_nhwc)
+    return ConvFn.apply(x_buf, w, bias, res_buf, act, out_fp32_nchw, pad, out_f32_nhwc, out_hw)
 
 
 class SpadeFn(torch.autograd.Function):
@@ -151,8 +153,7 @@ class SpadeFn(torch.autograd.Function):
             noise, nsd, mean, rstd, act, want_dgb=True)
         dactv = None
         if ctx.needs_input_grad[0]:
-            wcat = torch.stack([wg.detach(), wb.detach()], 1).reshape(2 * C, *wg.shape[1:])  # interleaved (gamma_c, beta_c) rows
-            pw = ops.pack_weight(wcat.flip(2, 3).transpose(0, 1).contiguous(), (1, 1))
+            pw = ops.pack_weight(wg, (1, 1), interleave=wb, dgrad=True)  # K = interleaved (gamma_c, beta_c) columns of dgb
             da = Act.empty(n, h, w, wg.shape[1], pitch=actv_buf.shape[3], zero=actv_buf.shape[3] > wg.shape[1])
             ops.conv2d(dgb, pw, da)
             dactv = da.buf
@@ -176,7 +177,7 @@ class FromNCHW(torch.autograd.Function):
         n, c, h, w = ctx.shape
         if ctx.size is not None and tuple(ctx.size) != (h, w):
             raise NotImplementedError("gradient through the nearest-resized input pyramid is never needed (inputs are data)")
-        return dbuf[..., :c].permute(0, 3, 1, 2).float().contiguous(), None, None
+        return Act(dbuf.contiguous(), c=c).to_nchw(), None, None
 
 
 def _block_train(blk, x0_buf, x0_shift, x1_buf, seg_buf, noise_fn, out_act):
@@ -224,14 +225,54 @@ def generator_forward_train(g, x, seg):
 
 # ------------------------------------------------------------------------------------------------ discriminator (training)
 
-def space_to_depth_t(x_buf):
-    """Differentiable space-to-depth by 2 with zero fill of odd edges, channel order (py*2+px)*C + c
-    (same convention as hrv_space_to_depth / ops.s2d_weight). torch reshapes: pure data movement."""
-    n, h, w, c = x_buf.shape
-    if (h | w) & 1:
-        x_buf = F.pad(x_buf, (0, 0, 0, w & 1, 0, h & 1))
-        n, h, w, c = x_buf.shape
-    return x_buf.reshape(n, h // 2, 2, w // 2, 2, c).permute(0, 1, 3, 2, 4, 5).reshape(n, h // 2, w // 2, 4 * c).contiguous()
+class S2DFn(torch.autograd.Function):
+    """Space-to-depth by 2 with zero fill of odd edges, channel order (py*2+px)*C8 + c (hrv_space_to_depth / ops.s2d_weight
+    convention) and its inverse gather as the backward: one kernel each way, no pad / permute copies."""
+
+    @staticmethod
+    def forward(ctx, x_buf, cin):
+        ctx.meta = (x_buf.shape, cin)
+        return ops.space_to_depth(Act(x_buf, c=cin)).buf
+
+    @staticmethod
+    def backward(ctx, d):
+        (n, h, w, p), cin = ctx.meta
+        dx = ops.space_to_depth_bwd(Act(d.contiguous()), n, h, w, cin, pitch=p)
+        if p > ops.round_up(cin, 8):
+            dx.buf[..., ops.round_up(cin, 8):] = 0
+        return dx.buf, None
+
+
+def space_to_depth_t(x_buf, cin=None):
+    return S2DFn.apply(x_buf, x_buf.shape[3] if cin is None else cin)
+
+
+class MaxPool2Fn(torch.autograd.Function):
+    """nn.MaxPool2d(2,2) on a pixel-major bf16 buffer (Vgg19, networks.py:201-231): hrv_maxpool2_fwd / hrv_maxpool2_bwd."""
+
+    @staticmethod
+    def forward(ctx, x_buf):
+        ctx.save_for_backward(x_buf)
+        return ops.maxpool2(Act(x_buf)).buf
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x_buf,) = ctx.saved_tensors
+        return ops.maxpool2_bwd(Act(x_buf), Act(dy.contiguous())).buf
+
+
+class AvgPool3S2Fn(torch.autograd.Function):
+    """F.avg_pool2d(3, stride 2, padding 1, count_include_pad=False) between discriminator scales (network_generator.py:302)
+    on the pixel-major bf16 buffer: hrv_avgpool3s2 / hrv_avgpool3s2_bwd."""
+
+    @staticmethod
+    def forward(ctx, x_buf):
+        ctx.hw = x_buf.shape[1:3]
+        return ops.avgpool3s2(Act(x_buf)).buf
+
+    @staticmethod
+    def backward(ctx, dy):
+        return ops.avgpool3s2_bwd(Act(dy.contiguous()), *ctx.hw).buf
 
 
 class InstNormActFn(torch.autograd.Function):
@@ -274,12 +315,10 @@ def _nlayer_train(d, x_buf, need_wgrad):
         last = i == d.n_groups - 1
         if convm.stride[0] == 2:
             w2 = ops.s2d_weight(w, 2) if not w.requires_grad else _s2d_weight_t(w)
-            src = space_to_depth_t(h)
-            # k4 s2 p2 on (H,W) == k2 s1 p1 on the space-to-depth tensor; extent floor(H/2)+1
-            y = conv(src, w2, bias, act=ACT_NONE if has_in else ACT_LRELU, pad=1)
-            oh, ow = h.shape[1] // 2 + 1, h.shape[2] // 2 + 1
-            if y.shape[1] != oh or y.shape[2] != ow:
-                y = y[:, :oh, :ow].contiguous()
+            src = space_to_depth_t(h, w.shape[1])
+            # k4 s2 p2 on (H,W) == k2 s1 p1 on the space-to-depth tensor; extent floor(H/2)+1 (one less than the s2d conv's
+            # natural extent when H is odd: the kernels simply do not compute / read the cropped row)
+            y = conv(src, w2, bias, act=ACT_NONE if has_in else ACT_LRELU, pad=1, out_hw=(h.shape[1] // 2 + 1, h.shape[2] // 2 + 1))
         else:
             y = conv(h, w, bias, pad=2, out_f32_nhwc=last)
         if has_in:
@@ -318,9 +357,7 @@ def discriminator_forward_train(D, input_nchw, need_wgrad=True, as_float=True):
             feats.append(v.float() if as_float else v)
         result.append(feats if not D.no_ganFeat_loss else [feats[-1]])
         if k + 1 < len(ds):
-            v = cur[..., :cin].permute(0, 3, 1, 2).float().contiguous()
-            v = F.avg_pool2d(v, 3, stride=2, padding=1, count_include_pad=False)
-            cur = FromNCHW.apply(v, None, None)
+            cur = AvgPool3S2Fn.apply(cur)
     return result
 
 
@@ -337,7 +374,7 @@ def vgg_features(vgg, x_nchw):
             if isinstance(layer, torch.nn.Conv2d):
                 h = conv(h, layer.weight, layer.bias, act=ACT_RELU)
             elif isinstance(layer, torch.nn.MaxPool2d):
-                h = F.max_pool2d(h.permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1).contiguous()
+                h = MaxPool2Fn.apply(h)
             elif isinstance(layer, torch.nn.ReLU):
                 pass  # fused into the preceding convolution's epilogue
             else:
@@ -348,9 +385,10 @@ def vgg_features(vgg, x_nchw):
 
 def vgg_loss(vgg, weights, x, y):
     """VGGLoss.forward (networks.py:244-251): sum_i w_i * L1(vgg_i(x), vgg_i(y).detach())."""
-    n = x.shape[0]
-    f = vgg_features(vgg, torch.cat([x, y.detach()], 0))  # one pass over both images
+    with torch.no_grad():  # the target branch carries no gradient: keep it out of the graph so the backward runs over x only
+        fy = vgg_features(vgg, y.detach())
+    fx = vgg_features(vgg, x)
     loss = 0
-    for wgt, t in zip(weights, f):
-        loss = loss + wgt * (t[:n].float() - t[n:].float().detach()).abs().mean()
+    for wgt, tx, ty in zip(weights, fx, fy):
+        loss = loss + wgt * (tx - ty).abs().mean(dtype=torch.float32)  # bf16 difference, fp32 accumulation
     return loss

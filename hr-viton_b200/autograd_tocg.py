@@ -8,7 +8,7 @@ import torch
 import torch.nn.functional as F
 
 from . import ops
-from .autograd_g import FromNCHW, InstNormActFn, conv, space_to_depth_t, _s2d_weight_t
+from .autograd_g import AvgPool3S2Fn, FromNCHW, InstNormActFn, conv, space_to_depth_t, _s2d_weight_t
 from .ops import ACT_LRELU, ACT_NONE, ACT_RELU, Act
 
 
@@ -106,11 +106,9 @@ def _resblock(rb, x_buf):
     """ResBlock.forward in training mode (networks.py:171-198)."""
     if rb.kind == "down":
         w = rb.scale.weight
-        src = space_to_depth_t(x_buf[..., :ops.round_up(w.shape[1], 8)].contiguous() if x_buf.shape[3] != ops.round_up(w.shape[1], 8) else x_buf)
-        r = conv(src, _s2d_weight_t(w), rb.scale.bias, pad=1)
-        oh, ow = (x_buf.shape[1] - 1) // 2 + 1, (x_buf.shape[2] - 1) // 2 + 1  # k3 s2 p1
-        if r.shape[1] != oh or r.shape[2] != ow:
-            r = r[:, :oh, :ow].contiguous()
+        src = space_to_depth_t(x_buf, w.shape[1])
+        oh, ow = (x_buf.shape[1] - 1) // 2 + 1, (x_buf.shape[2] - 1) // 2 + 1  # k3 s2 p1 extent; the s2d form would give one more
+        r = conv(src, _s2d_weight_t(w), rb.scale.bias, pad=1, out_hw=(oh, ow))
     elif rb.kind == "same":
         r = conv(x_buf, rb.scale.weight, rb.scale.bias, pad=0)
     else:
@@ -194,9 +192,7 @@ def _patch_sequence_train(seq, h, training):
             fused_act = ACT_LRELU if (has_lr and not has_in) else ACT_NONE
             if mod.stride[0] == 2:
                 oh, ow = h.shape[1] // 2 + 1, h.shape[2] // 2 + 1
-                y = conv(space_to_depth_t(h), _s2d_weight_t(w), mod.bias, act=fused_act, pad=1)
-                if y.shape[1] != oh or y.shape[2] != ow:
-                    y = y[:, :oh, :ow].contiguous()
+                y = conv(space_to_depth_t(h, w.shape[1]), _s2d_weight_t(w), mod.bias, act=fused_act, pad=1, out_hw=(oh, ow))
             else:
                 y = conv(h, w, mod.bias, act=fused_act, pad=2, out_f32_nhwc=last)
             if has_in:
@@ -215,14 +211,13 @@ def tocg_discriminator_forward_train(D, input_nchw):
     """networks.MultiscaleDiscriminator.forward (networks.py:331-349), getIntermFeat=False: list[num_D] of [logits NCHW fp32]."""
     if D.getIntermFeat:
         raise NotImplementedError("getIntermFeat=True training path is not built (the reference trains with getIntermFeat=False)")
-    x = input_nchw.float()
+    buf = FromNCHW.apply(input_nchw.float(), None, None)
     if D.Ddownx2:
-        x = F.avg_pool2d(x.contiguous(), 3, stride=2, padding=1, count_include_pad=False)
+        buf = AvgPool3S2Fn.apply(buf)
     res = []
     for i in range(D.num_D):
-        buf = FromNCHW.apply(x, None, None)
         o = _patch_sequence_train(getattr(D, "layer%d" % (D.num_D - 1 - i)), buf, D.training)
         res.append([o.permute(0, 3, 1, 2)])
         if i != D.num_D - 1:
-            x = F.avg_pool2d(x.contiguous(), 3, stride=2, padding=1, count_include_pad=False)
+            buf = AvgPool3S2Fn.apply(buf)
     return res

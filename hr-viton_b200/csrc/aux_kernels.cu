@@ -675,3 +675,51 @@ extern "C" int hrv_flow_warp_bwd(const float* flow_lo, const float* lin_x, const
   }
   return HRV_OK;
 }
+
+// ------------------------------------------------------------------------------------------------ weight packing
+namespace hrv {
+// One pass from the fp32 parameter layout (cout,cin,kh,kw) to the bf16 GEMM layout [taps][n_pad][cin_k] (zero padded), with
+// optional 1/sigma scaling, (gamma,beta) row interleave of two parameters and the flip+transpose of the data-gradient convolution.
+__global__ void pack_conv_weight_kernel(const float* __restrict__ w0, const float* __restrict__ w1, int cout, int cin, int kh, int kw,
+                                        int transpose_flip, const float* __restrict__ inv_scale, __nv_bfloat16* __restrict__ dst,
+                                        int n_pad, int cin_k, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = (int)(idx % cin_k);
+  const int n = (int)((idx / cin_k) % n_pad);
+  const int tap = (int)(idx / ((long long)cin_k * n_pad));
+  const int ky = tap / kw, kx = tap - ky * kw;
+  const int inter = w1 ? 2 : 1;
+  float v = 0.f;
+  if (!transpose_flip) {
+    // GEMM row n = output channel (interleaved pair index), K index c = input channel
+    if (n < cout * inter && c < cin) {
+      const float* src = (w1 && (n & 1)) ? w1 : w0;
+      const int co = n / inter;
+      v = src[(((long long)co * cin + c) * kh + ky) * kw + kx];
+    }
+  } else {
+    // data-gradient conv: GEMM row n = original INPUT channel, K index c = original OUTPUT channel (interleaved), taps flipped
+    if (n < cin && c < cout * inter) {
+      const float* src = (w1 && (c & 1)) ? w1 : w0;
+      const int co = c / inter;
+      v = src[(((long long)co * cin + n) * kh + (kh - 1 - ky)) * kw + (kw - 1 - kx)];
+    }
+  }
+  if (inv_scale) v *= __ldg(inv_scale);
+  dst[idx] = __float2bfloat16(v);
+}
+}  // namespace hrv
+
+extern "C" int hrv_pack_conv_weight(const float* w0, const float* w1, int32_t cout, int32_t cin, int32_t kh, int32_t kw,
+                                    int32_t transpose_flip, const float* inv_scale, void* dst, int32_t n_pad, int32_t cin_k,
+                                    hrv_stream stream) {
+  if (!w0 || !dst || cout < 1 || cin < 1 || kh < 1 || kw < 1) return set_error(HRV_EINVAL, "pack_conv_weight: bad arguments");
+  const int inter = w1 ? 2 : 1;
+  const int rows = transpose_flip ? cin : cout * inter, cols = transpose_flip ? cout * inter : cin;
+  if (n_pad < rows || cin_k < cols) return set_error(HRV_EINVAL, "pack_conv_weight: destination too small (%d x %d for %d x %d)", n_pad, cin_k, rows, cols);
+  const long long total = (long long)kh * kw * n_pad * cin_k;
+  pack_conv_weight_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(w0, w1, cout, cin, kh, kw, transpose_flip, inv_scale,
+                                                                                   (__nv_bfloat16*)dst, n_pad, cin_k, total);
+  return launch_ok("pack_conv_weight");
+}

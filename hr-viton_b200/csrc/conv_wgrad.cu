@@ -160,7 +160,7 @@ extern "C" int hrv_conv2d_wgrad(const hrv_tensor* x, const hrv_tensor* dy, int32
   if (((uintptr_t)x->ptr & 15) || ((uintptr_t)dy->ptr & 15) || (x->pitch % 8) || (dy->pitch % 8))
     return set_error(HRV_EINVAL, "wgrad: 16-byte alignment and pitch %% 8 == 0 required");
   if (kh < 1 || kw < 1 || kw > 4 || x->n != dy->n) return set_error(HRV_EINVAL, "wgrad: bad geometry");
-  if (dy->h != x->h + 2 * pad - kh + 1 || dy->w != x->w + 2 * pad - kw + 1) return set_error(HRV_EINVAL, "wgrad: dy extent != conv output extent");
+  if (dy->h > x->h + 2 * pad - kh + 1 || dy->w > x->w + 2 * pad - kw + 1) return set_error(HRV_EINVAL, "wgrad: dy extent exceeds the conv output extent");  // smaller = cropped output
   WgradArgs a;
   memset(&a, 0, sizeof(a));
   a.Nimg = x->n; a.OH = dy->h; a.OW = dy->w; a.xsegs = (dy->w + kPX - 1) / kPX;

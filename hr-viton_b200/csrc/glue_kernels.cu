@@ -1,0 +1,273 @@
+// glue_kernels.cu — data-movement / pooling kernels either side of the convolutions in the TRAINING step
+// (SURVEY.md §8 rows N1/N2): space-to-depth backward, 2x2 max-pool (VGG19) forward/backward, 3x3/s2 average-pool backward
+// (multi-scale discriminator), and the fused "upsample -> 15x15 Gaussian -> argmax -> 7-class one-hot" of the parse map
+// (train_generator.py:247-273).  All HBM-bound: one 16-byte vector (8 bf16 channels) per thread, coalesced along channels.
+#include "hrv_host.h"
+#include "hrv_ptx.cuh"
+
+namespace hrv {
+namespace {
+
+struct GView {
+  const void* ptr;
+  int n, h, w, c, pitch;
+};
+GView gv(const hrv_tensor* t) { return GView{t->ptr, t->n, t->h, t->w, t->c, t->pitch}; }
+
+int check_vec(const hrv_tensor* t, const char* what) {
+  if (!t || !t->ptr) return set_error(HRV_EINVAL, "%s: null tensor", what);
+  if (t->dtype != HRV_BF16) return set_error(HRV_EINVAL, "%s: must be bf16 NHWC", what);
+  if (((uintptr_t)t->ptr & 15) || (t->pitch % 8) || t->pitch < t->c) return set_error(HRV_EINVAL, "%s: needs a 16-byte aligned ptr and pitch %% 8 == 0", what);
+  return HRV_OK;
+}
+int launched(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? HRV_OK : set_error(HRV_ECUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+unsigned nblocks(long long total, int threads) { return (unsigned)((total + threads - 1) / threads); }
+
+__device__ __forceinline__ uint4 ld16(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ void st16(__nv_bfloat16* p, const uint4& v) { *reinterpret_cast<uint4*>(p) = v; }
+__device__ __forceinline__ void un8(const uint4& u, float (&f)[8]) {
+  f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
+  f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
+}
+__device__ __forceinline__ uint4 pk8(const float (&f)[8]) {
+  return make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+}
+__device__ __forceinline__ const __nv_bfloat16* at(const GView& v, int n, int y, int x) {
+  return reinterpret_cast<const __nv_bfloat16*>(v.ptr) + (((long long)n * v.h + y) * v.w + x) * v.pitch;
+}
+__device__ __forceinline__ __nv_bfloat16* at_w(const GView& v, int n, int y, int x) { return const_cast<__nv_bfloat16*>(at(v, n, y, x)); }
+
+// ---------------------------------------------------------------------------------------------- space-to-depth backward
+// dx[n,y,x,g*8..] = d[n, y/2, x/2, ((y&1)*2 + (x&1)) * C8 + g*8..]     thread = (dx pixel, channel group)
+__global__ void space_to_depth_bwd_kernel(GView d, GView dx, int G, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int g = (int)(idx % G);
+  const long long pix = idx / G;
+  const int x = (int)(pix % dx.w), y = (int)((pix / dx.w) % dx.h), n = (int)(pix / ((long long)dx.w * dx.h));
+  const int sub = ((y & 1) << 1) | (x & 1);
+  st16(at_w(dx, n, y, x) + g * 8, ld16(at(d, n, y >> 1, x >> 1) + (sub * G + g) * 8));
+}
+
+// ---------------------------------------------------------------------------------------------- 2x2 max-pool (stride 2, floor)
+__global__ void maxpool2_fwd_kernel(GView x, GView y, int G, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int g = (int)(idx % G);
+  const long long pix = idx / G;
+  const int X = (int)(pix % y.w), Y = (int)((pix / y.w) % y.h), n = (int)(pix / ((long long)y.w * y.h));
+  const __nv_bfloat16* p = at(x, n, 2 * Y, 2 * X) + g * 8;
+  const long long row = (long long)x.w * x.pitch;
+  const uint4 a = ld16(p), b = ld16(p + x.pitch), c = ld16(p + row), d = ld16(p + row + x.pitch);
+  float fa[8], fb[8], fc[8], fd[8], o[8];
+  un8(a, fa); un8(b, fb); un8(c, fc); un8(d, fd);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[i] = fmaxf(fmaxf(fa[i], fb[i]), fmaxf(fc[i], fd[i]));
+  st16(at_w(y, n, Y, X) + g * 8, pk8(o));
+}
+// The gradient goes to the FIRST maximum of the window in row-major order (what the library's index-based backward does).
+__global__ void maxpool2_bwd_kernel(GView x, GView dy, GView dx, int G, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int g = (int)(idx % G);
+  const long long pix = idx / G;
+  const int X = (int)(pix % dy.w), Y = (int)((pix / dy.w) % dy.h), n = (int)(pix / ((long long)dy.w * dy.h));
+  const __nv_bfloat16* p = at(x, n, 2 * Y, 2 * X) + g * 8;
+  const long long row = (long long)x.w * x.pitch;
+  float f[4][8], gy[8], o[4][8];
+  un8(ld16(p), f[0]); un8(ld16(p + x.pitch), f[1]); un8(ld16(p + row), f[2]); un8(ld16(p + row + x.pitch), f[3]);
+  un8(ld16(at(dy, n, Y, X) + g * 8), gy);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int best = 0;
+    float m = f[0][i];
+#pragma unroll
+    for (int k = 1; k < 4; ++k)
+      if (f[k][i] > m) { m = f[k][i]; best = k; }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) o[k][i] = (k == best) ? gy[i] : 0.f;
+  }
+  __nv_bfloat16* q = at_w(dx, n, 2 * Y, 2 * X) + g * 8;
+  const long long qrow = (long long)dx.w * dx.pitch;
+  st16(q, pk8(o[0])); st16(q + dx.pitch, pk8(o[1])); st16(q + qrow, pk8(o[2])); st16(q + qrow + dx.pitch, pk8(o[3]));
+}
+
+// ---------------------------------------------------------------------------------------------- avg-pool 3x3/s2/p1 backward
+// count_include_pad=False: dx[y,x] = sum over windows (Y,X) containing (y,x) of dy[Y,X] / valid(Y,X).  thread = (dx pixel, group)
+__global__ void avgpool3s2_bwd_kernel(GView dy, GView dx, int G, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int g = (int)(idx % G);
+  const long long pix = idx / G;
+  const int x = (int)(pix % dx.w), y = (int)((pix / dx.w) % dx.h), n = (int)(pix / ((long long)dx.w * dx.h));
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const int Y0 = y >> 1, Y1 = (y & 1) ? Y0 + 1 : Y0, X0 = x >> 1, X1 = (x & 1) ? X0 + 1 : X0;
+  for (int Y = Y0; Y <= Y1; ++Y) {
+    if (Y >= dy.h) continue;
+    const int rows = min(2 * Y + 1, dx.h - 1) - max(2 * Y - 1, 0) + 1;
+    for (int X = X0; X <= X1; ++X) {
+      if (X >= dy.w) continue;
+      const int cols = min(2 * X + 1, dx.w - 1) - max(2 * X - 1, 0) + 1;
+      float v[8];
+      un8(ld16(at(dy, n, Y, X) + g * 8), v);
+      const float inv = 1.f / (float)(rows * cols);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += v[i] * inv;
+    }
+  }
+  st16(at_w(dx, n, y, x) + g * 8, pk8(acc));
+}
+
+// ---------------------------------------------------------------------------------------------- parse map: up -> blur -> argmax
+// seg: fp32 NCHW (n,C,h,w) low-resolution class scores.  For every output pixel of the (H,W) grid:
+//   u_c   = bilinear(seg_c) (align_corners=False, F.interpolate semantics)              train_generator.py:247
+//   b_c   = 15x15 Gaussian(sigma 3), zero padding, separable                               train_generator.py:154,247
+//   k     = argmax_c b_c  (first maximum)                                                  train_generator.py:248
+// outputs: idx (n,H,W) int64 and/or onehot (n,groups,H,W) fp32 with onehot[group_of[k]] = 1   train_generator.py:251-273
+constexpr int kTile = 32, kHalo = 7, kU = kTile + 2 * kHalo;  // 46
+struct ParseArgs {
+  const float* seg;
+  long long* idx;
+  float* onehot;
+  int n, C, h, w, H, W, groups;
+  float sy, sx;
+  float g[15];
+  int group_of[32];
+};
+__global__ void __launch_bounds__(256) parse_blur_argmax_kernel(const __grid_constant__ ParseArgs a) {
+  __shared__ float U[kU][kU + 1];
+  __shared__ float Hb[kU][kTile + 1];
+  const int n = blockIdx.z, ty0 = blockIdx.y * kTile, tx0 = blockIdx.x * kTile;
+  const int tid = threadIdx.x;
+  const int col = tid & 31, rq = tid >> 5;  // thread owns output rows rq, rq+8, rq+16, rq+24 of column col
+  float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+  int arg[4] = {0, 0, 0, 0};
+  for (int c = 0; c < a.C; ++c) {
+    const float* s = a.seg + ((long long)n * a.C + c) * a.h * a.w;
+    for (int i = tid; i < kU * kU; i += 256) {
+      const int uy = i / kU, ux = i - uy * kU;
+      const int Y = ty0 + uy - kHalo, X = tx0 + ux - kHalo;
+      float v = 0.f;
+      if (Y >= 0 && Y < a.H && X >= 0 && X < a.W) {
+        const float fy = fmaxf(a.sy * ((float)Y + 0.5f) - 0.5f, 0.f), fx = fmaxf(a.sx * ((float)X + 0.5f) - 0.5f, 0.f);
+        const int y0 = (int)fy, x0 = (int)fx;
+        const int y1 = min(y0 + 1, a.h - 1), x1 = min(x0 + 1, a.w - 1);
+        const float ly = fy - (float)y0, lx = fx - (float)x0;
+        const float v00 = __ldg(s + y0 * a.w + x0), v01 = __ldg(s + y0 * a.w + x1), v10 = __ldg(s + y1 * a.w + x0), v11 = __ldg(s + y1 * a.w + x1);
+        v = (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
+      }
+      U[uy][ux] = v;
+    }
+    __syncthreads();
+    for (int i = tid; i < kU * kTile; i += 256) {
+      const int uy = i >> 5, x = i & 31;
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < 15; ++k) acc = fmaf(a.g[k], U[uy][x + k], acc);
+      Hb[uy][x] = acc;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int y = rq + 8 * j;
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < 15; ++k) acc = fmaf(a.g[k], Hb[y + k][col], acc);
+      if (acc > best[j]) { best[j] = acc; arg[j] = c; }
+    }
+    // U / Hb are rewritten by the next channel: the barrier after the U fill separates Hb readers from Hb writers,
+    // but U writers of channel c+1 must wait for the horizontal pass of channel c -> already ordered by the 2nd barrier.
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int Y = ty0 + rq + 8 * j, X = tx0 + col;
+    if (Y < a.H && X < a.W) {
+      const long long p = ((long long)n * a.H + Y) * a.W + X;
+      if (a.idx) a.idx[p] = arg[j];
+      if (a.onehot) {
+        const int grp = a.group_of[arg[j]];
+        for (int q = 0; q < a.groups; ++q) a.onehot[(((long long)n * a.groups + q) * a.H + Y) * a.W + X] = (q == grp) ? 1.f : 0.f;
+      }
+    }
+  }
+}
+
+}  // namespace
+}  // namespace hrv
+
+using namespace hrv;
+
+extern "C" int hrv_space_to_depth_bwd(const hrv_tensor* d, const hrv_tensor* dx, hrv_stream stream) {
+  int rc;
+  if ((rc = check_vec(d, "s2d_bwd d")) || (rc = check_vec(dx, "s2d_bwd dx"))) return rc;
+  const int G = (dx->c + 7) / 8;
+  if (d->n != dx->n || d->h != (dx->h + 1) / 2 || d->w != (dx->w + 1) / 2 || d->pitch < 4 * G * 8 || dx->pitch < G * 8)
+    return set_error(HRV_EINVAL, "s2d_bwd: extents (d %dx%dx%d for dx %dx%dx%d)", d->h, d->w, d->c, dx->h, dx->w, dx->c);
+  const long long total = (long long)dx->n * dx->h * dx->w * G;
+  if (total) space_to_depth_bwd_kernel<<<nblocks(total, 256), 256, 0, (cudaStream_t)stream>>>(gv(d), gv(dx), G, total);
+  return launched("space_to_depth_bwd");
+}
+
+extern "C" int hrv_maxpool2_fwd(const hrv_tensor* x, const hrv_tensor* y, hrv_stream stream) {
+  int rc;
+  if ((rc = check_vec(x, "maxpool x")) || (rc = check_vec(y, "maxpool y"))) return rc;
+  if (y->n != x->n || y->h != x->h / 2 || y->w != x->w / 2 || y->c != x->c) return set_error(HRV_EINVAL, "maxpool: y must be (n, h/2, w/2, c)");
+  const int G = (x->c + 7) / 8;
+  const long long total = (long long)y->n * y->h * y->w * G;
+  if (total) maxpool2_fwd_kernel<<<nblocks(total, 256), 256, 0, (cudaStream_t)stream>>>(gv(x), gv(y), G, total);
+  return launched("maxpool2_fwd");
+}
+
+extern "C" int hrv_maxpool2_bwd(const hrv_tensor* x, const hrv_tensor* dy, const hrv_tensor* dx, hrv_stream stream) {
+  int rc;
+  if ((rc = check_vec(x, "maxpool_bwd x")) || (rc = check_vec(dy, "maxpool_bwd dy")) || (rc = check_vec(dx, "maxpool_bwd dx"))) return rc;
+  if (dy->n != x->n || dy->h != x->h / 2 || dy->w != x->w / 2 || dy->c != x->c || dx->n != x->n || dx->h != x->h || dx->w != x->w || dx->c != x->c)
+    return set_error(HRV_EINVAL, "maxpool_bwd: extents");
+  if ((x->h | x->w) & 1) {  // rows / columns the floor-mode pool never reads get a zero gradient
+    cudaError_t e = cudaMemsetAsync(const_cast<void*>(dx->ptr), 0, (size_t)dx->n * dx->h * dx->w * dx->pitch * 2, (cudaStream_t)stream);
+    if (e != cudaSuccess) return set_error(HRV_ECUDA, "maxpool_bwd memset: %s", cudaGetErrorString(e));
+  }
+  const int G = (x->c + 7) / 8;
+  const long long total = (long long)dy->n * dy->h * dy->w * G;
+  if (total) maxpool2_bwd_kernel<<<nblocks(total, 256), 256, 0, (cudaStream_t)stream>>>(gv(x), gv(dy), gv(dx), G, total);
+  return launched("maxpool2_bwd");
+}
+
+extern "C" int hrv_avgpool3s2_bwd(const hrv_tensor* dy, const hrv_tensor* dx, hrv_stream stream) {
+  int rc;
+  if ((rc = check_vec(dy, "avgpool_bwd dy")) || (rc = check_vec(dx, "avgpool_bwd dx"))) return rc;
+  if (dy->n != dx->n || dy->h != (dx->h - 1) / 2 + 1 || dy->w != (dx->w - 1) / 2 + 1) return set_error(HRV_EINVAL, "avgpool_bwd: extents");
+  const int G = (dx->c + 7) / 8;
+  if (dy->pitch < G * 8) return set_error(HRV_EINVAL, "avgpool_bwd: dy has fewer channel groups than dx");
+  const long long total = (long long)dx->n * dx->h * dx->w * G;
+  if (total) avgpool3s2_bwd_kernel<<<nblocks(total, 256), 256, 0, (cudaStream_t)stream>>>(gv(dy), gv(dx), G, total);
+  return launched("avgpool3s2_bwd");
+}
+
+extern "C" int hrv_parse_blur_argmax(const float* seg, int32_t n, int32_t c, int32_t h, int32_t w, int32_t H, int32_t W,
+                                     const int32_t* group_of, int32_t groups, int64_t* idx, float* onehot, hrv_stream stream) {
+  if (!seg || (!idx && !onehot) || n < 1 || c < 1 || c > 32 || h < 1 || w < 1 || H < 1 || W < 1)
+    return set_error(HRV_EINVAL, "parse_blur_argmax: bad arguments (c must be <= 32)");
+  if (onehot && (!group_of || groups < 1)) return set_error(HRV_EINVAL, "parse_blur_argmax: onehot needs group_of / groups");
+  ParseArgs a;
+  memset(&a, 0, sizeof(a));
+  a.seg = seg; a.idx = (long long*)idx; a.onehot = onehot;
+  a.n = n; a.C = c; a.h = h; a.w = w; a.H = H; a.W = W; a.groups = groups;
+  a.sy = (float)h / (float)H; a.sx = (float)w / (float)W;
+  double g[15], sum = 0;
+  for (int k = 0; k < 15; ++k) { g[k] = (double)expf(-(float)((k - 7) * (k - 7)) / 18.f); sum += g[k]; }
+  float fsum = 0.f;
+  for (int k = 0; k < 15; ++k) fsum += (float)g[k];
+  (void)sum;
+  for (int k = 0; k < 15; ++k) a.g[k] = (float)g[k] / fsum;
+  for (int k = 0; k < c; ++k) {
+    a.group_of[k] = group_of ? group_of[k] : k;
+    if (onehot && (a.group_of[k] < 0 || a.group_of[k] >= groups)) return set_error(HRV_EINVAL, "parse_blur_argmax: group_of[%d] out of range", k);
+  }
+  dim3 grid((W + kTile - 1) / kTile, (H + kTile - 1) / kTile, n);
+  parse_blur_argmax_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+  return launched("parse_blur_argmax");
+}

@@ -140,21 +140,32 @@ class PackedConv:
     flops_per_pixel: float = 0.0  # algorithmic 2*Cin*Cout*kh*kw of the ORIGINAL convolution (unpadded, pre-s2d)
 
 
-def pack_weight(w, off, cin_total=None, interleave=None, bn=None, flops_per_pixel=None):
-    """w: (Cout,Cin,kh,kw) fp32 cuda (already divided by sigma / transformed). Returns PackedConv.
-    interleave: a second weight of identical shape whose rows are interleaved (gamma_c, beta_c pairs)."""
+def pack_weight(w, off, cin_total=None, interleave=None, bn=None, flops_per_pixel=None, dgrad=False):
+    """w: (Cout,Cin,kh,kw) fp32 cuda (already divided by sigma / transformed). Returns PackedConv (one kernel: hrv_pack_conv_weight).
+    interleave: a second weight of identical shape whose rows are interleaved (gamma_c, beta_c pairs).
+    dgrad=True packs the operand of the data-gradient convolution (flip + transpose) without materialising it."""
+    w = w.detach()
+    if w.dtype != torch.float32 or not w.is_contiguous():
+        w = w.float().contiguous()
     if interleave is not None:
-        w = torch.stack([w, interleave], 1).reshape(2 * w.shape[0], *w.shape[1:])
+        interleave = interleave.detach()
+        if interleave.dtype != torch.float32 or not interleave.is_contiguous():
+            interleave = interleave.float().contiguous()
+        assert interleave.shape == w.shape
     cout, cin, kh, kw = w.shape
-    cin_eff = cin if cin_total is None else cin_total
-    bk = pick_bk(cin_eff)
-    cin_k = round_up(cin_eff, bk)
-    bn = pick_bn(cout) if bn is None else bn
-    n_pad = round_up(cout, bn)
-    wp = torch.zeros((kh * kw, n_pad, cin_k), dtype=torch.bfloat16, device=w.device)
-    wp[:, :cout, :cin] = w.permute(2, 3, 0, 1).reshape(kh * kw, cout, cin).to(torch.bfloat16)
-    fpp = 2.0 * cin * cout * kh * kw if flops_per_pixel is None else flops_per_pixel
-    return PackedConv(wp, kh, kw, off[0], off[1], bk, bn, cout, cin_eff, fpp)
+    inter = 2 if interleave is not None else 1
+    rows, cols = (cin, cout * inter) if dgrad else (cout * inter, cin)  # GEMM N rows, K columns
+    k_eff = cols if cin_total is None else cin_total
+    bk = pick_bk(k_eff)
+    cin_k = round_up(k_eff, bk)
+    bn = pick_bn(rows) if bn is None else bn
+    n_pad = round_up(rows, bn)
+    wp = torch.empty((kh * kw, n_pad, cin_k), dtype=torch.bfloat16, device=w.device)
+    capi.check(capi.lib().hrv_pack_conv_weight(w.data_ptr(), _p(interleave), cout, cin, kh, kw, 1 if dgrad else 0, None, wp.data_ptr(),
+                                               n_pad, cin_k, _stream()), "pack_conv_weight")
+    LAUNCHES[0] += 1
+    fpp = 2.0 * cin * cout * inter * kh * kw if flops_per_pixel is None else flops_per_pixel
+    return PackedConv(wp, kh, kw, off[0], off[1], bk, bn, rows, k_eff, fpp)
 
 
 def s2d_weight(w, pad):
@@ -276,6 +287,54 @@ def space_to_depth(x):
     capi.check(capi.lib().hrv_space_to_depth(ctypes.byref(tx), ctypes.byref(ty), _stream()), "space_to_depth")
     LAUNCHES[0] += 1
     return out
+
+
+def space_to_depth_bwd(d, n, h, w, c, pitch=None):
+    """dx (n,h,w,c) of space_to_depth from the gradient d of its (n,ceil(h/2),ceil(w/2),4*c8) output."""
+    dx = Act.empty(n, h, w, c, pitch=pitch)
+    td, tx = d.ct(), dx.ct()
+    capi.check(capi.lib().hrv_space_to_depth_bwd(ctypes.byref(td), ctypes.byref(tx), _stream()), "space_to_depth_bwd")
+    LAUNCHES[0] += 1
+    return dx
+
+
+def maxpool2(x):
+    y = Act.empty(x.n, x.h // 2, x.w // 2, x.c, pitch=x.pitch if x.c0 == 0 else None)
+    tx, ty = x.ct(), y.ct()
+    capi.check(capi.lib().hrv_maxpool2_fwd(ctypes.byref(tx), ctypes.byref(ty), _stream()), "maxpool2_fwd")
+    LAUNCHES[0] += 1
+    return y
+
+
+def maxpool2_bwd(x, dy):
+    dx = Act.empty(x.n, x.h, x.w, x.c, pitch=x.pitch if x.c0 == 0 else None)
+    tx, tdy, tdx = x.ct(), dy.ct(), dx.ct()
+    capi.check(capi.lib().hrv_maxpool2_bwd(ctypes.byref(tx), ctypes.byref(tdy), ctypes.byref(tdx), _stream()), "maxpool2_bwd")
+    LAUNCHES[0] += 1
+    return dx
+
+
+def avgpool3s2_bwd(dy, h, w):
+    dx = Act.empty(dy.n, h, w, dy.c, pitch=dy.pitch if dy.c0 == 0 else None)
+    tdy, tdx = dy.ct(), dx.ct()
+    capi.check(capi.lib().hrv_avgpool3s2_bwd(ctypes.byref(tdy), ctypes.byref(tdx), _stream()), "avgpool3s2_bwd")
+    LAUNCHES[0] += 1
+    return dx
+
+
+def parse_blur_argmax(seg, size, group_of=None, groups=0, want_idx=True):
+    """seg (n,c,h,w) fp32 cuda -> (idx (n,1,H,W) int64 | None, onehot (n,groups,H,W) fp32 | None); hrv_parse_blur_argmax."""
+    assert seg.is_cuda and seg.dtype == torch.float32
+    seg = seg.contiguous()
+    n, c, h, w = seg.shape
+    H, W = size
+    idx = torch.empty((n, 1, H, W), dtype=torch.int64, device=seg.device) if want_idx else None
+    onehot = torch.empty((n, groups, H, W), dtype=torch.float32, device=seg.device) if group_of is not None else None
+    garr = (ctypes.c_int32 * c)(*group_of) if group_of is not None else None
+    capi.check(capi.lib().hrv_parse_blur_argmax(seg.data_ptr(), n, c, h, w, H, W, garr, groups, _p(idx), _p(onehot), _stream()),
+               "parse_blur_argmax")
+    LAUNCHES[0] += 1
+    return idx, onehot
 
 
 def avgpool3s2(x):

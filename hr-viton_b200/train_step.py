@@ -9,6 +9,7 @@ import torch.nn.functional as F
 
 _GRID_CACHE = {}
 LABELS7 = [[0], [2, 4, 7, 8, 9, 10, 11], [3], [1], [5], [6], [12]]  # train_generator.py:261-269
+GROUP_OF_13 = [next(i for i, grp in enumerate(LABELS7) if k in grp) for k in range(13)]
 
 
 def gaussian_blur_15_3(x):
@@ -22,8 +23,10 @@ def gaussian_blur_15_3(x):
     return F.conv2d(x, g.view(1, 1, 15, 1).expand(c, 1, 15, 1), padding=(7, 0), groups=c)
 
 
-def make_generator_inputs(tocg, batch, fine_h, fine_w, occlusion=False):
-    """train_generator.py:201-275 (opt.GT False, clothmask_composition 'warp_grad')."""
+def make_generator_inputs(tocg, batch, fine_h, fine_w, occlusion=False, unfused_parse=False):
+    """train_generator.py:201-275 (opt.GT False, clothmask_composition 'warp_grad').
+    unfused_parse=True keeps the parse-map post-processing as the separate torch ops of the reference (what the tests use to
+    check the fused kernel, also on CPU tensors); the product path is the kernel and needs CUDA tensors."""
     from .tocg import make_grid
     cm, c_paired = batch["cloth_mask"], batch["cloth"]
     with torch.no_grad():
@@ -47,20 +50,25 @@ def make_generator_inputs(tocg, batch, fine_h, fine_w, occlusion=False):
         warped_grid = grid + flow_norm
         warped_cloth = F.grid_sample(c_paired, warped_grid, padding_mode="border", align_corners=False)
         warped_clothmask = F.grid_sample(cm, warped_grid, padding_mode="border", align_corners=False)
-        fake_parse_gauss = gaussian_blur_15_3(F.interpolate(fake_segmap, size=(ih, iw), mode="bilinear"))
-        fake_parse = fake_parse_gauss.argmax(dim=1)[:, None]
-        if occlusion:
-            so = F.softmax(fake_parse_gauss, dim=1)
-            warped_clothmask = warped_clothmask - torch.cat([so[:, 1:3], so[:, 5:]], 1).sum(1, keepdim=True) * warped_clothmask
-            warped_cloth = warped_cloth * warped_clothmask + (1 - warped_clothmask)
-        old_parse = torch.zeros(n, 13, fine_h, fine_w, device=cm.device).scatter_(1, fake_parse, 1.0)
-        mkey = ("regroup", str(cm.device))
-        if mkey not in _GRID_CACHE:  # 13 -> 7 class regrouping as a constant 7x13 0/1 matrix (train_generator.py:261-273)
-            m = torch.zeros(7, 13)
-            for i, idx in enumerate(LABELS7):
-                m[i, idx] = 1.0
-            _GRID_CACHE[mkey] = m.to(cm.device)
-        parse = torch.einsum("ij,njhw->nihw", _GRID_CACHE[mkey], old_parse)
+        if occlusion or unfused_parse:
+            fake_parse_gauss = gaussian_blur_15_3(F.interpolate(fake_segmap, size=(ih, iw), mode="bilinear"))
+            fake_parse = fake_parse_gauss.argmax(dim=1)[:, None]
+            if occlusion:
+                so = F.softmax(fake_parse_gauss, dim=1)
+                warped_clothmask = warped_clothmask - torch.cat([so[:, 1:3], so[:, 5:]], 1).sum(1, keepdim=True) * warped_clothmask
+                warped_cloth = warped_cloth * warped_clothmask + (1 - warped_clothmask)
+            old_parse = torch.zeros(n, 13, fine_h, fine_w, device=cm.device).scatter_(1, fake_parse, 1.0)
+            mkey = ("regroup", str(cm.device))
+            if mkey not in _GRID_CACHE:  # 13 -> 7 class regrouping as a constant 7x13 0/1 matrix (train_generator.py:261-273)
+                m = torch.zeros(7, 13)
+                for i, idx in enumerate(LABELS7):
+                    m[i, idx] = 1.0
+                _GRID_CACHE[mkey] = m.to(cm.device)
+            parse = torch.einsum("ij,njhw->nihw", _GRID_CACHE[mkey], old_parse)
+        else:
+            # bilinear resize -> 15x15 Gaussian -> argmax -> one-hot -> 13->7 regroup (train_generator.py:247-273) in one kernel
+            from . import ops
+            _, parse = ops.parse_blur_argmax(fake_segmap.float(), (ih, iw), group_of=GROUP_OF_13, groups=7, want_idx=False)
         g_in = torch.cat((batch["agnostic"], batch["densepose"], warped_cloth), 1)
     return g_in.detach(), parse.detach()
 

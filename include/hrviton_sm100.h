@@ -175,6 +175,33 @@ int hrv_bilinear_up2_bwd(const hrv_tensor* dout, const hrv_tensor* da, hrv_strea
 int hrv_flow_warp_bwd(const float* flow_lo, const float* lin_x, const float* lin_y, const hrv_tensor* src, const hrv_tensor* ddst,
                       float* dsrc32, float* dflow_up, float* dflow_lo, hrv_stream stream);
 
+/* ---- training-step glue: pooling / re-layout backward passes and the parse-map post-processing ---- */
+
+/* Backward of hrv_space_to_depth: dx[n,y,x,c] = d[n, y/2, x/2, ((y&1)*2+(x&1))*C8 + c], C8 = 8*ceil(dx.c/8). */
+int hrv_space_to_depth_bwd(const hrv_tensor* d, const hrv_tensor* dx, hrv_stream stream);
+
+/* nn.MaxPool2d(2, 2) of Vgg19 (networks.py:201-231) on NHWC bf16: y = (n, h/2, w/2, c) (floor mode). The backward routes dy to
+ * the first maximum of each window (recomputed from x; no index tensor). */
+int hrv_maxpool2_fwd(const hrv_tensor* x, const hrv_tensor* y, hrv_stream stream);
+int hrv_maxpool2_bwd(const hrv_tensor* x, const hrv_tensor* dy, const hrv_tensor* dx, hrv_stream stream);
+
+/* Backward of hrv_avgpool3s2 (count_include_pad=False): dx (n,h,w,c) from dy (n,(h-1)/2+1,(w-1)/2+1,c). */
+int hrv_avgpool3s2_bwd(const hrv_tensor* dy, const hrv_tensor* dx, hrv_stream stream);
+
+/* train_generator.py:247-273 in one kernel: bilinear resize of the (n,c,h,w) fp32 class scores to (H,W) (align_corners=False),
+ * 15x15 Gaussian blur (sigma 3, zero padding; tgm.image.GaussianBlur), arg-max over classes (first maximum).
+ * idx (optional): (n,H,W) int64 class ids.  onehot (optional): (n,groups,H,W) fp32, channel group_of[class] set to 1
+ * (group_of: HOST array of c entries; the 13 -> 7 label regrouping). */
+int hrv_parse_blur_argmax(const float* seg, int32_t n, int32_t c, int32_t h, int32_t w, int32_t H, int32_t W,
+                          const int32_t* group_of, int32_t groups, int64_t* idx, float* onehot, hrv_stream stream);
+
+/* fp32 parameter (cout,cin,kh,kw) -> bf16 GEMM operand [kh*kw][n_pad][cin_k] of hrv_conv2d_fwd, zero padded, in one pass.
+ * w1 (optional): second parameter of identical shape whose rows are interleaved with w0's (row 2c = w0[c], 2c+1 = w1[c]: the
+ * SPADE gamma|beta GEMM).  transpose_flip != 0 packs the operand of the data-gradient convolution instead (rows = input channels,
+ * K = output channels, taps mirrored).  inv_scale (optional, device scalar) multiplies every element (1/sigma of spectral norm). */
+int hrv_pack_conv_weight(const float* w0, const float* w1, int32_t cout, int32_t cin, int32_t kh, int32_t kw,
+                         int32_t transpose_flip, const float* inv_scale, void* dst, int32_t n_pad, int32_t cin_k, hrv_stream stream);
+
 /* Library / device introspection. */
 const char* hrv_last_error(void);
 int hrv_version(void);

@@ -297,7 +297,7 @@ def test_stage2_losses_match_oracle_pipeline():
         return t
 
     with torch.no_grad():
-        g_in_r, parse_r = train_step.make_generator_inputs(_OracleTocg(), batch, h, w)
+        g_in_r, parse_r = train_step.make_generator_inputs(_OracleTocg(), batch, h, w, unfused_parse=True)
         out_r = orc.spade_generator_forward(sdg, g_in_r, parse_r, noise_cpu)
         pred_r = orc.gen_d_forward(sdd, torch.cat((torch.cat((parse_r, out_r), 1), torch.cat((parse_r, batch["image"]), 1)), 0))
         fake_r = [[t[:n] for t in p] for p in pred_r]

@@ -245,3 +245,105 @@ def test_conv_wgrad(case):
     err = rel_err(got, ref)
     print("wgrad rel err", case, err)
     assert err < 2e-3
+
+
+# ------------------------------------------------------------------------------------------------ training-step glue kernels
+
+def _to_buf(x_nchw, pitch=None):
+    """fp32 NCHW (cpu) -> (N,H,W,P) bf16 cuda buffer with zero pad channels."""
+    n, c, h, w = x_nchw.shape
+    p = ops.round_up(c, 8) if pitch is None else pitch
+    buf = torch.zeros((n, h, w, p), dtype=torch.bfloat16, device=DEV)
+    buf[..., :c] = x_nchw.permute(0, 2, 3, 1).to(DEV).to(torch.bfloat16)
+    return buf
+
+
+@pytest.mark.parametrize("shape", [(2, 10, 13, 9), (1, 64, 8, 12), (3, 24, 7, 7)])
+def test_space_to_depth_bwd_is_the_adjoint(shape):
+    """<S(x), d> == <x, S^T(d)> for exactly representable values, plus the explicit index formula."""
+    n, c, h, w = shape
+    c8 = ops.round_up(c, 8)
+    h2, w2 = (h + 1) // 2, (w + 1) // 2
+    d = bf16r(synth.normalish((n, h2, w2, 4 * c8), 3, "d")).to(DEV).to(torch.bfloat16).contiguous()
+    dx = ops.space_to_depth_bwd(Act(d), n, h, w, c).buf.float().cpu()
+    dref = d.float().cpu().reshape(n, h2, w2, 2, 2, c8)
+    for y in range(h):
+        for x in range(w):
+            assert torch.equal(dx[:, y, x, :c], dref[:, y // 2, x // 2, y & 1, x & 1, :c]), (y, x)
+    # forward/backward pair consistency on a one-hot probe
+    xb = _to_buf(bf16r(synth.normalish(shape, 4, "x")))
+    s = ops.space_to_depth(Act(xb, c=c)).buf
+    back = ops.space_to_depth_bwd(Act(s), n, h, w, c).buf
+    assert torch.equal(back[..., :c], xb[..., :c])
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 16, 12), (1, 24, 9, 7), (2, 8, 2, 2)])
+def test_maxpool2_fwd_bwd(shape):
+    n, c, h, w = shape
+    x = bf16r(synth.normalish(shape, 5, "x")).requires_grad_(True)
+    ref = F.max_pool2d(x, 2)
+    g = bf16r(synth.normalish(tuple(ref.shape), 5, "g"))
+    ref.backward(g)
+    xb = _to_buf(x.detach())
+    y = ops.maxpool2(Act(xb))
+    assert torch.equal(y.buf[..., :c].float().cpu(), ref.detach().permute(0, 2, 3, 1))
+    dx = ops.maxpool2_bwd(Act(xb), Act(_to_buf(g)))
+    assert torch.equal(dx.buf[..., :c].float().cpu(), x.grad.permute(0, 2, 3, 1))
+
+
+@pytest.mark.parametrize("shape", [(2, 10, 16, 12), (1, 19, 9, 7), (1, 8, 2, 3)])
+def test_avgpool3s2_bwd(shape):
+    n, c, h, w = shape
+    x = bf16r(synth.normalish(shape, 6, "x")).requires_grad_(True)
+    ref = F.avg_pool2d(x, 3, stride=2, padding=1, count_include_pad=False)
+    g = bf16r(synth.normalish(tuple(ref.shape), 6, "g"))
+    ref.backward(g)
+    dx = ops.avgpool3s2_bwd(Act(_to_buf(g)), h, w)
+    got = dx.buf[..., :c].float().cpu()
+    want = x.grad.permute(0, 2, 3, 1)
+    assert float((got - want).abs().max()) <= 2 ** -8 * float(want.abs().max()) + 1e-6  # one bf16 rounding of the result
+
+
+def test_parse_blur_argmax_matches_the_torch_pipeline():
+    """train_generator.py:247-273: resize -> Gaussian -> argmax -> one-hot regroup.  The fused kernel must pick the same class
+    as the unfused fp32 pipeline except where the two top scores are within float rounding of each other."""
+    from hrviton_b200 import train_step
+    n, H, W = 2, 160, 96
+    seg = synth.normalish((n, 13, 40, 24), 7, "seg").to(DEV)
+    idx, onehot = ops.parse_blur_argmax(seg, (H, W), group_of=train_step.GROUP_OF_13, groups=7)
+    up = F.interpolate(seg, size=(H, W), mode="bilinear")
+    gauss = train_step.gaussian_blur_15_3(up)
+    ref = gauss.argmax(1, keepdim=True)
+    diff = idx != ref
+    if bool(diff.any()):  # disagreements only at numerical ties of the two best classes
+        top2 = gauss.topk(2, dim=1).values
+        gap = (top2[:, 0] - top2[:, 1])[diff[:, 0]]
+        assert float(gap.max()) < 1e-5, float(gap.max())
+    assert float(diff.float().mean()) < 1e-3
+    # one-hot output == regrouped one-hot of the kernel's own arg-max (exact)
+    m = torch.zeros(7, 13, device=DEV)
+    for i, grp in enumerate(train_step.LABELS7):
+        m[i, grp] = 1.0
+    old = torch.zeros(n, 13, H, W, device=DEV).scatter_(1, idx, 1.0)
+    assert torch.equal(onehot, torch.einsum("ij,njhw->nihw", m, old))
+    # a non multiple-of-tile extent
+    idx2, _ = ops.parse_blur_argmax(seg, (50, 45))
+    ref2 = train_step.gaussian_blur_15_3(F.interpolate(seg, size=(50, 45), mode="bilinear")).argmax(1, keepdim=True)
+    assert float((idx2 != ref2).float().mean()) < 2e-3
+
+
+@pytest.mark.parametrize("dgrad", [False, True])
+@pytest.mark.parametrize("inter", [False, True])
+def test_pack_conv_weight(dgrad, inter):
+    cout, cin, k = 20, 13, 3
+    w0 = synth.normalish((cout, cin, k, k), 8, "w0").to(DEV)
+    w1 = synth.normalish((cout, cin, k, k), 8, "w1").to(DEV) if inter else None
+    pw = ops.pack_weight(w0, (1, 1), interleave=w1, dgrad=dgrad)
+    full = torch.stack([w0, w1], 1).reshape(2 * cout, cin, k, k) if inter else w0  # interleaved rows
+    if dgrad:
+        full = full.flip(2, 3).transpose(0, 1)  # (cin, cout*, kh, kw)
+    rows, cols = full.shape[:2]
+    want = torch.zeros_like(pw.w, dtype=torch.float32)
+    want[:, :rows, :cols] = full.permute(2, 3, 0, 1).reshape(k * k, rows, cols)
+    assert pw.n_gemm == rows
+    assert torch.equal(pw.w.float(), want.to(torch.bfloat16).float())
