@@ -34,6 +34,17 @@ def gen_opt():
                                  fine_height=H, fine_width=W, cuda=True)
 
 
+def conv_traffic():
+    """Average DRAM bytes (read+write) per conv_igemm launch of one step, from the committed ncu pass
+    (profiles/r1_conv_dram_traffic.json, written by tools/summarise_ncu_traffic.py); None when that pass was not taken."""
+    p = os.path.join(ROOT, "profiles", "r1_conv_dram_traffic.json")
+    try:
+        with open(p) as f:
+            return json.load(f)["avg_dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -388,11 +399,13 @@ def main():
     # ---- per-kernel profile pass (CUDA events around every C-ABI launch) -> roofline of the dominant kernel
     ops.PROFILE = []
     torch.cuda.synchronize()
+    torch.cuda.nvtx.range_push("hrv_profile_step")  # `ncu --nvtx --nvtx-include "hrv_profile_step/"` = launch list of ONE step
     if train:
         trainer.step(batch_d, H, W)  # eager (events cannot be recorded inside a graph replay)
     else:
         step_resident()
     torch.cuda.synchronize()
+    torch.cuda.nvtx.range_pop()
     prof = ops.PROFILE
     ops.PROFILE = None
     agg = {}
@@ -414,7 +427,7 @@ def main():
     achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
     roofline = {"kernel": "conv_igemm_kernel (tcgen05 implicit-GEMM conv, all %d launches of one step)" % conv_launches,
                 "bound": "tensor", "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["tf_sustained"], "traffic": None, "peak_source": peaks["src"] + " (bf16 sustained)",
+                "frac": achieved / peaks["tf_sustained"], "traffic": conv_traffic(), "peak_source": peaks["src"] + " (bf16 sustained)",
                 "avg_launch_ms": conv_ms / max(1, conv_launches), "algorithmic_gflop_per_launch": conv_flops / 1e9 / max(1, conv_launches)}
     total_prof_ms = sum(a[1] for a in agg.values())
     breakdown = {k: {"ms": round(a[1], 3), "launches": a[2], "share": round(a[1] / total_prof_ms, 4)} for k, a in agg.items()}
@@ -433,7 +446,7 @@ def main():
                 "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
                 "data": "synthetic",
                 "config": {"workload": ("train_stage1: full train_condition.py step (tocg fwd+bwd with train-mode BatchNorm, 3 stage-1 D passes fwd+bwd, VGG loss x5 fwd+dgrad, L1/TV/CE/LSGAN, Adam x2; README flags --Ddownx2 --Ddropout --lasttvonly --interflowloss --occlusion), 1024x768, bf16 activations / fp32 accumulate" if (train and stage1) else
-                                        "train_stage2: full train_generator.py step (tocg fwd, G fwd+bwd, D fwd+bwd x2, 2nd G fwd, VGG loss fwd+dgrad, Adam x2), 1024x768, bf16 activations / fp32 accumulate; convs (fwd/dgrad/wgrad), norms, modulation, activations on this repo's kernels; resampling glue, max-pool, losses, Adam = torch"
+                                        "train_stage2: full train_generator.py step (tocg fwd, G fwd+bwd, D fwd+bwd x2, 2nd G fwd, VGG loss fwd+dgrad, Adam x2), 1024x768, bf16 activations / fp32 accumulate; convs (fwd/dgrad/wgrad), norms, modulation, activations, pooling, weight packing, parse-map glue, VGG L1 on this repo's kernels; hi-res grid_sample, hinge/feature-matching reductions, spectral-norm power iteration, Adam = torch"
                                         if train else "gen_fwd: SPADEGenerator inference forward, 1024x768, bf16 activations, fp32 accumulate"),
                            "launch": ("cuda-graph replay of the whole step" if (train and use_graph) else "eager"), "per_gpu_batch": B, "global_batch": B * world, "parallelism": "dp%d" % world,
                            "l2": "activations per step (>10 GB) exceed the 126 MB L2; no explicit flush",

@@ -180,14 +180,27 @@ class FromNCHW(torch.autograd.Function):
         return Act(dbuf.contiguous(), c=c).to_nchw(), None, None
 
 
+def im2col_weight(w, k_pad):
+    """(cout,cin,kh,kw) -> (cout,k_pad,1,1) in the tap-major column order of hrv_im2col (differentiable index shuffle)."""
+    cout, cin, kh, kw = w.shape
+    return F.pad(w.permute(0, 2, 3, 1).reshape(cout, kh * kw * cin), (0, k_pad - kh * kw * cin)).reshape(cout, k_pad, 1, 1)
+
+
 def _block_train(blk, x0_buf, x0_shift, x1_buf, seg_buf, noise_fn, out_act):
     """SPADEResBlock forward with autograd nodes (network_generator.py:157-173)."""
     from .spade import _conv_weight_train
     n, h, w, _ = seg_buf.shape
+    seg_c = blk.norm_0.conv_shared[0].weight.shape[1]
+    # 3x3 over the few-channel label map: gather the 9 taps once per block (shared by its 2-3 norms) so each mlp_shared
+    # convolution is a single K=64 GEMM block per pixel tile and its weight gradient a 1x1 GEMM
+    cols = ops.im2col(Act(seg_buf, c=seg_c), 3, 3, 1).buf if 9 * seg_c <= 64 else None
 
     def spade(norm, x0b, sh, x1b, act):
         cs = norm.conv_shared[0]
-        actv = conv(seg_buf, cs.weight, cs.bias, act=ACT_RELU)
+        if cols is not None:
+            actv = conv(cols, im2col_weight(cs.weight, cols.shape[3]), cs.bias, act=ACT_RELU, pad=0)
+        else:
+            actv = conv(seg_buf, cs.weight, cs.bias, act=ACT_RELU)
         return SpadeFn.apply(actv, norm.conv_gamma.weight, norm.conv_beta.weight, norm.conv_gamma.bias, norm.conv_beta.bias,
                              x0b, x1b, noise_fn(n, h, w), norm.noise_scale, sh, act)
 
@@ -383,6 +396,21 @@ def vgg_features(vgg, x_nchw):
     return outs
 
 
+class L1MeanFn(torch.autograd.Function):
+    """mean |a - b| over two pixel-major bf16 buffers (b carries no gradient): hrv_l1_sum / hrv_l1_bwd, one pass each."""
+
+    @staticmethod
+    def forward(ctx, a_buf, b_buf):
+        ctx.save_for_backward(a_buf, b_buf)
+        return (ops.l1_sum(Act(a_buf), Act(b_buf)) / a_buf.numel()).float().reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        a_buf, b_buf = ctx.saved_tensors
+        gscale = (g.float() / a_buf.numel()).reshape(1).contiguous()
+        return ops.l1_bwd(Act(a_buf), Act(b_buf), gscale).buf, None
+
+
 def vgg_loss(vgg, weights, x, y):
     """VGGLoss.forward (networks.py:244-251): sum_i w_i * L1(vgg_i(x), vgg_i(y).detach())."""
     with torch.no_grad():  # the target branch carries no gradient: keep it out of the graph so the backward runs over x only
@@ -390,5 +418,5 @@ def vgg_loss(vgg, weights, x, y):
     fx = vgg_features(vgg, x)
     loss = 0
     for wgt, tx, ty in zip(weights, fx, fy):
-        loss = loss + wgt * (tx - ty).abs().mean(dtype=torch.float32)  # bf16 difference, fp32 accumulation
+        loss = loss + wgt * L1MeanFn.apply(tx, ty)
     return loss

@@ -682,32 +682,28 @@ namespace hrv {
 // optional 1/sigma scaling, (gamma,beta) row interleave of two parameters and the flip+transpose of the data-gradient convolution.
 __global__ void pack_conv_weight_kernel(const float* __restrict__ w0, const float* __restrict__ w1, int cout, int cin, int kh, int kw,
                                         int transpose_flip, const float* __restrict__ inv_scale, __nv_bfloat16* __restrict__ dst,
-                                        int n_pad, int cin_k, long long total) {
+                                        int n_pad, int cin_k, long long plane) {
+  // thread = one (row n, K index c) of the GEMM operand; it walks the kh*kw taps, i.e. reads the taps of one (co,ci) pair from
+  // CONTIGUOUS fp32 memory and writes one bf16 per tap plane (coalesced across the threads of a warp, which vary c).
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
+  if (idx >= plane) return;
   const int c = (int)(idx % cin_k);
-  const int n = (int)((idx / cin_k) % n_pad);
-  const int tap = (int)(idx / ((long long)cin_k * n_pad));
-  const int ky = tap / kw, kx = tap - ky * kw;
+  const int n = (int)(idx / cin_k);
   const int inter = w1 ? 2 : 1;
-  float v = 0.f;
+  const int taps = kh * kw;
+  const float* src = nullptr;
   if (!transpose_flip) {
     // GEMM row n = output channel (interleaved pair index), K index c = input channel
-    if (n < cout * inter && c < cin) {
-      const float* src = (w1 && (n & 1)) ? w1 : w0;
-      const int co = n / inter;
-      v = src[(((long long)co * cin + c) * kh + ky) * kw + kx];
-    }
+    if (n < cout * inter && c < cin) src = ((w1 && (n & 1)) ? w1 : w0) + ((long long)(n / inter) * cin + c) * taps;
   } else {
-    // data-gradient conv: GEMM row n = original INPUT channel, K index c = original OUTPUT channel (interleaved), taps flipped
-    if (n < cin && c < cout * inter) {
-      const float* src = (w1 && (c & 1)) ? w1 : w0;
-      const int co = c / inter;
-      v = src[(((long long)co * cin + n) * kh + (kh - 1 - ky)) * kw + (kw - 1 - kx)];
-    }
+    // data-gradient conv: GEMM row n = original INPUT channel, K index c = original OUTPUT channel (interleaved), taps mirrored
+    if (n < cin && c < cout * inter) src = ((w1 && (c & 1)) ? w1 : w0) + ((long long)(c / inter) * cin + n) * taps;
   }
-  if (inv_scale) v *= __ldg(inv_scale);
-  dst[idx] = __float2bfloat16(v);
+  const float sc = inv_scale ? __ldg(inv_scale) : 1.f;
+  for (int tap = 0; tap < taps; ++tap) {
+    const float v = src ? __ldg(src + (transpose_flip ? taps - 1 - tap : tap)) * sc : 0.f;
+    dst[(long long)tap * plane + idx] = __float2bfloat16(v);
+  }
 }
 }  // namespace hrv
 
@@ -718,8 +714,8 @@ extern "C" int hrv_pack_conv_weight(const float* w0, const float* w1, int32_t co
   const int inter = w1 ? 2 : 1;
   const int rows = transpose_flip ? cin : cout * inter, cols = transpose_flip ? cout * inter : cin;
   if (n_pad < rows || cin_k < cols) return set_error(HRV_EINVAL, "pack_conv_weight: destination too small (%d x %d for %d x %d)", n_pad, cin_k, rows, cols);
-  const long long total = (long long)kh * kw * n_pad * cin_k;
-  pack_conv_weight_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(w0, w1, cout, cin, kh, kw, transpose_flip, inv_scale,
-                                                                                   (__nv_bfloat16*)dst, n_pad, cin_k, total);
+  const long long plane = (long long)n_pad * cin_k;
+  pack_conv_weight_kernel<<<blocks_for(plane, 256), 256, 0, (cudaStream_t)stream>>>(w0, w1, cout, cin, kh, kw, transpose_flip, inv_scale,
+                                                                                   (__nv_bfloat16*)dst, n_pad, cin_k, plane);
   return launch_ok("pack_conv_weight");
 }

@@ -195,6 +195,111 @@ __global__ void __launch_bounds__(256) parse_blur_argmax_kernel(const __grid_con
   }
 }
 
+// ---------------------------------------------------------------------------------------------- im2col for tiny-Cin convolutions
+// dst[n,y,x, tap*C + ci] = src[n, y+ky-pad, x+kx-pad, ci] (zero outside / beyond taps*C).  A 3x3 convolution over a 7-channel
+// label map (SPADE's mlp_shared, network_generator.py:182-184) becomes ONE K=64 GEMM block per pixel tile instead of nine K=16
+// taps, and its weight gradient a plain 1x1 GEMM.  thread = (pixel, 8-channel group of dst)
+__global__ void im2col_kernel(GView src, GView dst, int kh, int kw, int pad, int Gd, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int g = (int)(idx % Gd);
+  const long long pix = idx / Gd;
+  const int x = (int)(pix % dst.w), y = (int)((pix / dst.w) % dst.h), n = (int)(pix / ((long long)dst.w * dst.h));
+  const int K = kh * kw * src.c;
+  const unsigned short* s = reinterpret_cast<const unsigned short*>(src.ptr);
+  unsigned short v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int j = g * 8 + i;
+    unsigned short o = 0;
+    if (j < K) {
+      const int tap = j / src.c, ci = j - tap * src.c;
+      const int ky = tap / kw, kx = tap - ky * kw;
+      const int sy = y + ky - pad, sx = x + kx - pad;
+      if (sy >= 0 && sy < src.h && sx >= 0 && sx < src.w) o = __ldg(s + (((long long)n * src.h + sy) * src.w + sx) * src.pitch + ci);
+    }
+    v[i] = o;
+  }
+  uint4 o4;
+  o4.x = v[0] | ((unsigned)v[1] << 16); o4.y = v[2] | ((unsigned)v[3] << 16); o4.z = v[4] | ((unsigned)v[5] << 16); o4.w = v[6] | ((unsigned)v[7] << 16);
+  st16(at_w(dst, n, y, x) + g * 8, o4);
+}
+
+// 3x3 / 7-channel specialisation (the SPADE label map): thread = pixel; nine 16-byte loads (one per tap, the 8th lane is the
+// buffer's zero pad channel), the 63 values are re-packed with compile-time indices, eight 16-byte stores (128 contiguous bytes).
+__device__ __forceinline__ uint32_t half_of(const uint4& u, int ci) {
+  const uint32_t w = ci < 2 ? u.x : (ci < 4 ? u.y : (ci < 6 ? u.z : u.w));
+  return (ci & 1) ? (w >> 16) : (w & 0xFFFFu);
+}
+__global__ void __launch_bounds__(256) im2col3x3_c7_kernel(GView src, GView dst, long long npix) {
+  const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= npix) return;
+  const int x = (int)(pix % dst.w), y = (int)((pix / dst.w) % dst.h), n = (int)(pix / ((long long)dst.w * dst.h));
+  uint4 t[9];
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const int sy = y + tap / 3 - 1, sx = x + tap % 3 - 1;
+    t[tap] = (sy >= 0 && sy < src.h && sx >= 0 && sx < src.w) ? ld16(at(src, n, sy, sx)) : make_uint4(0, 0, 0, 0);
+  }
+  __nv_bfloat16* o = at_w(dst, n, y, x);
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    uint32_t w[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int j0 = g * 8 + 2 * q, j1 = j0 + 1;
+      const uint32_t lo = j0 < 63 ? half_of(t[j0 / 7], j0 % 7) : 0u;
+      const uint32_t hi = j1 < 63 ? half_of(t[j1 / 7], j1 % 7) : 0u;
+      w[q] = lo | (hi << 16);
+    }
+    st16(o + g * 8, make_uint4(w[0], w[1], w[2], w[3]));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- L1 feature loss
+// sum |a - b| over the (n,h,w,c) views (fp64 accumulator), and its gradient da = sign(a - b) * (*gscale).
+__global__ void __launch_bounds__(256) l1_fwd_kernel(GView a, GView b, int G, long long total, double* __restrict__ out) {
+  float acc = 0.f;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(idx % G);
+    const long long pix = idx / G;
+    float fa[8], fb[8];
+    un8(ld16(reinterpret_cast<const __nv_bfloat16*>(a.ptr) + pix * a.pitch + g * 8), fa);
+    un8(ld16(reinterpret_cast<const __nv_bfloat16*>(b.ptr) + pix * b.pitch + g * 8), fb);
+    const int lim = min(8, a.c - g * 8);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i < lim) acc += fabsf(fa[i] - fb[i]);
+  }
+  __shared__ float red[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < 8; ++i) t += (double)red[i];
+    atomicAdd(out, t);
+  }
+}
+__global__ void l1_bwd_kernel(GView a, GView b, GView da, int G, long long total, const float* __restrict__ gscale) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int g = (int)(idx % G);
+  const long long pix = idx / G;
+  const float gs = __ldg(gscale);
+  float fa[8], fb[8], o[8];
+  un8(ld16(reinterpret_cast<const __nv_bfloat16*>(a.ptr) + pix * a.pitch + g * 8), fa);
+  un8(ld16(reinterpret_cast<const __nv_bfloat16*>(b.ptr) + pix * b.pitch + g * 8), fb);
+  const int lim = min(8, a.c - g * 8);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float d = fa[i] - fb[i];
+    o[i] = (i < lim) ? (d > 0.f ? gs : (d < 0.f ? -gs : 0.f)) : 0.f;
+  }
+  st16(reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(da.ptr)) + pix * da.pitch + g * 8, pk8(o));
+}
+
 }  // namespace
 }  // namespace hrv
 
@@ -270,4 +375,53 @@ extern "C" int hrv_parse_blur_argmax(const float* seg, int32_t n, int32_t c, int
   dim3 grid((W + kTile - 1) / kTile, (H + kTile - 1) / kTile, n);
   parse_blur_argmax_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
   return launched("parse_blur_argmax");
+}
+
+extern "C" int hrv_im2col(const hrv_tensor* src, const hrv_tensor* dst, int32_t kh, int32_t kw, int32_t pad, hrv_stream stream) {
+  int rc;
+  if ((rc = check_vec(src, "im2col src")) || (rc = check_vec(dst, "im2col dst"))) return rc;
+  if (kh < 1 || kw < 1 || dst->n != src->n || dst->h != src->h || dst->w != src->w || dst->c < kh * kw * src->c || (dst->c % 8))
+    return set_error(HRV_EINVAL, "im2col: dst must be (n,h,w, >= kh*kw*c, multiple of 8)");
+  const int Gd = dst->c / 8;
+  const long long total = (long long)dst->n * dst->h * dst->w * Gd;
+  const long long npix = (long long)dst->n * dst->h * dst->w;
+  if (kh == 3 && kw == 3 && pad == 1 && src->c == 7 && dst->c == 64) {
+    if (npix) im2col3x3_c7_kernel<<<nblocks(npix, 256), 256, 0, (cudaStream_t)stream>>>(gv(src), gv(dst), npix);
+  } else if (total) {
+    im2col_kernel<<<nblocks(total, 256), 256, 0, (cudaStream_t)stream>>>(gv(src), gv(dst), kh, kw, pad, Gd, total);
+  }
+  return launched("im2col");
+}
+
+static int l1_check(const hrv_tensor* a, const hrv_tensor* b) {
+  int rc;
+  if ((rc = check_vec(a, "l1 a")) || (rc = check_vec(b, "l1 b"))) return rc;
+  if (a->n != b->n || a->h != b->h || a->w != b->w || a->c != b->c) return set_error(HRV_EINVAL, "l1: shape mismatch");
+  return HRV_OK;
+}
+
+extern "C" int hrv_l1_sum(const hrv_tensor* a, const hrv_tensor* b, double* sum, hrv_stream stream) {
+  int rc;
+  if ((rc = l1_check(a, b))) return rc;
+  if (!sum) return set_error(HRV_EINVAL, "l1_sum: null accumulator");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(sum, 0, sizeof(double), st);
+  const int G = (a->c + 7) / 8;
+  const long long total = (long long)a->n * a->h * a->w * G;
+  if (total) {
+    long long want = (total + 255) / 256;
+    const long long cap = (long long)sm_count() * 16;
+    l1_fwd_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(gv(a), gv(b), G, total, sum);
+  }
+  return launched("l1_sum");
+}
+
+extern "C" int hrv_l1_bwd(const hrv_tensor* a, const hrv_tensor* b, const float* gscale, const hrv_tensor* da, hrv_stream stream) {
+  int rc;
+  if ((rc = l1_check(a, b)) || (rc = l1_check(a, da))) return rc;
+  if (!gscale) return set_error(HRV_EINVAL, "l1_bwd: null gscale");
+  const int G = (a->c + 7) / 8;
+  const long long total = (long long)a->n * a->h * a->w * G;
+  if (total) l1_bwd_kernel<<<nblocks(total, 256), 256, 0, (cudaStream_t)stream>>>(gv(a), gv(b), gv(da), G, total, gscale);
+  return launched("l1_bwd");
 }

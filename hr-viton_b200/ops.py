@@ -322,6 +322,36 @@ def avgpool3s2_bwd(dy, h, w):
     return dx
 
 
+def im2col(x, kh, kw, pad, k_pad=None):
+    """(n,h,w,c) -> (n,h,w,K) with K = round_up(kh*kw*c, 64|32|16): the tap-major column form of a tiny-Cin convolution."""
+    k = kh * kw * x.c
+    if k_pad is None:
+        k_pad = round_up(k, 64) if k > 32 else (32 if k > 16 else 16)
+    out = Act.empty(x.n, x.h, x.w, k_pad)
+    tx, to = x.ct(), out.ct()
+    capi.check(capi.lib().hrv_im2col(ctypes.byref(tx), ctypes.byref(to), kh, kw, pad, _stream()), "im2col")
+    LAUNCHES[0] += 1
+    return out
+
+
+def l1_sum(a, b):
+    """sum |a - b| as a 1-element fp64 cuda tensor."""
+    out = torch.empty(1, dtype=torch.float64, device=a.buf.device)
+    ta, tb = a.ct(), b.ct()
+    capi.check(capi.lib().hrv_l1_sum(ctypes.byref(ta), ctypes.byref(tb), out.data_ptr(), _stream()), "l1_sum")
+    LAUNCHES[0] += 1
+    return out
+
+
+def l1_bwd(a, b, gscale):
+    """da = sign(a - b) * gscale (gscale: 1-element fp32 cuda tensor)."""
+    da = Act.empty(a.n, a.h, a.w, a.c, pitch=a.pitch if a.c0 == 0 else None)
+    ta, tb, td = a.ct(), b.ct(), da.ct()
+    capi.check(capi.lib().hrv_l1_bwd(ctypes.byref(ta), ctypes.byref(tb), gscale.data_ptr(), ctypes.byref(td), _stream()), "l1_bwd")
+    LAUNCHES[0] += 1
+    return da
+
+
 def parse_blur_argmax(seg, size, group_of=None, groups=0, want_idx=True):
     """seg (n,c,h,w) fp32 cuda -> (idx (n,1,H,W) int64 | None, onehot (n,groups,H,W) fp32 | None); hrv_parse_blur_argmax."""
     assert seg.is_cuda and seg.dtype == torch.float32

@@ -347,3 +347,37 @@ def test_pack_conv_weight(dgrad, inter):
     want[:, :rows, :cols] = full.permute(2, 3, 0, 1).reshape(k * k, rows, cols)
     assert pw.n_gemm == rows
     assert torch.equal(pw.w.float(), want.to(torch.bfloat16).float())
+
+
+@pytest.mark.parametrize("shape", [(2, 7, 12, 9), (1, 3, 8, 8)])
+def test_im2col_conv_equals_direct_conv(shape):
+    """hrv_im2col + 1x1 GEMM == the 3x3 convolution it replaces (same products, fp32 accumulation)."""
+    from hrviton_b200 import autograd_g
+    n, c, h, w = shape
+    x = bf16r(synth.normalish(shape, 9, "x"))
+    wt = bf16r(synth.normalish((24, c, 3, 3), 9, "w", 0.2))
+    cols = ops.im2col(Act(_to_buf(x), c=c), 3, 3, 1)
+    # explicit column check against unfold (channel-major in torch -> tap-major here)
+    unf = F.unfold(x, 3, padding=1).reshape(n, c, 9, h, w).permute(0, 3, 4, 2, 1).reshape(n, h, w, 9 * c)
+    assert torch.equal(cols.buf[..., :9 * c].float().cpu(), unf)
+    assert float(cols.buf[..., 9 * c:].float().abs().max()) == 0.0
+    wc = autograd_g.im2col_weight(wt.to(DEV), cols.c)
+    out = Act.empty(n, h, w, 24)
+    ops.conv2d(cols, ops.pack_weight(wc, (0, 0)), out)
+    ref = F.conv2d(x, wt, padding=1)
+    assert rel_err(out.to_nchw(), ref) < 1e-2
+
+
+def test_l1_sum_and_bwd():
+    shape = (2, 24, 9, 7)
+    a = bf16r(synth.normalish(shape, 10, "a")).requires_grad_(True)
+    b = bf16r(synth.normalish(shape, 10, "b"))
+    ref = (a - b).abs().mean()
+    ref.backward()
+    A, B = Act(_to_buf(a.detach())), Act(_to_buf(b))
+    s = ops.l1_sum(A, B)
+    assert abs(float(s) / a.numel() - float(ref)) < 1e-6
+    gs = torch.full((1,), 0.5 / a.numel(), device=DEV)
+    da = ops.l1_bwd(A, B, gs).buf.float().cpu().permute(0, 3, 1, 2)
+    want = (a.grad * 0.5).to(torch.bfloat16).float()
+    assert torch.equal(da, want)

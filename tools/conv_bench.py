@@ -11,7 +11,8 @@ cases = [  # cin, cout(n_gemm), k, h, w, spade
     (128, 160, 3, 1024, 768, True), (128, 288, 3, 512, 384, True), (128, 544, 3, 256, 192, True), (128, 64, 3, 1024, 768, True),
     (80, 32, 3, 1024, 768, False), (80, 32, 1, 1024, 768, False), (32, 32, 3, 1024, 768, False), (144, 64, 3, 512, 384, False),
     (7, 384, 3, 1024, 768, False), (9, 16, 3, 1024, 768, False), (32, 3, 3, 1024, 768, False), (1040, 512, 3, 64, 48, False),
-    (272, 128, 3, 256, 192, False), (528, 256, 3, 128, 96, False)]
+    (272, 128, 3, 256, 192, False), (528, 256, 3, 128, 96, False),
+    (64, 384, 1, 1024, 768, False), (64, 128, 1, 1024, 768, False), (160, 128, 3, 1024, 768, False), (192, 128, 3, 1024, 768, False)]
 for cin, cout, k, h, w, spade in cases:
     x = Act(torch.randn(B, h, w, ops.round_up(cin, 8), device="cuda").to(torch.bfloat16), c=cin)
     wt = torch.randn(cout // (2 if spade else 1), cin, k, k, device="cuda") * 0.05
@@ -38,7 +39,8 @@ for cin, cout, k, h, w, spade in cases:
     print("%4d->%4d k%d %4dx%-4d %s  %7.3f ms  %7.1f TFLOP/s" % (cin, cout, k, h, w, "spade " if spade else "linear", ms, fl / ms / 1e9), flush=True)
 
 # weight-gradient kernel on the same layer shapes
-for cin, cout, k, h, w in [(128, 160, 3, 1024, 768), (128, 288, 3, 512, 384), (80, 32, 3, 1024, 768), (1040, 512, 3, 64, 48), (256, 256, 3, 256, 192)]:
+for cin, cout, k, h, w in [(128, 160, 3, 1024, 768), (128, 288, 3, 512, 384), (80, 32, 3, 1024, 768), (1040, 512, 3, 64, 48), (256, 256, 3, 256, 192),
+                          (64, 128, 1, 1024, 768), (7, 128, 3, 1024, 768), (160, 128, 3, 1024, 768), (64, 64, 3, 1024, 768)]:
     x = Act(torch.randn(B, h, w, ops.round_up(cin, 8), device="cuda").to(torch.bfloat16), c=cin)
     dy = Act(torch.randn(B, h, w, ops.round_up(cout, 8), device="cuda").to(torch.bfloat16), c=cout)
     fn = lambda: ops.conv2d_wgrad(x, dy, k, k, k // 2)
