@@ -399,13 +399,15 @@ def main():
     # ---- per-kernel profile pass (CUDA events around every C-ABI launch) -> roofline of the dominant kernel
     ops.PROFILE = []
     torch.cuda.synchronize()
-    torch.cuda.nvtx.range_push("hrv_profile_step")  # `ncu --nvtx --nvtx-include "hrv_profile_step/"` = launch list of ONE step
+    # process-wide start/end range (the backward runs on autograd's own thread, which a push/pop range would not cover):
+    # `ncu --nvtx --nvtx-include "hrv_profile_step" ...` = launch list of exactly ONE step of this command
+    nvtx_id = torch.cuda.nvtx.range_start("hrv_profile_step")
     if train:
         trainer.step(batch_d, H, W)  # eager (events cannot be recorded inside a graph replay)
     else:
         step_resident()
     torch.cuda.synchronize()
-    torch.cuda.nvtx.range_pop()
+    torch.cuda.nvtx.range_end(nvtx_id)
     prof = ops.PROFILE
     ops.PROFILE = None
     agg = {}

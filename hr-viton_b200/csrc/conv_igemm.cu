@@ -58,6 +58,7 @@ struct alignas(64) ConvArgs {
   int C_mod;
   __nv_bfloat16* gamma_out;
   int gamma_pitch;
+  int pairs, tiles_m, store_c;  // pixel-N variant: 256-pixel tiles (pairs of 128-pixel boxes), channels written per pixel
 };
 
 template <int BK>
@@ -462,6 +463,226 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
   }
 }
 
+// ------------------------------------------------------------------------------------------------ pixel-N variant
+// tcgen05.mma (both operands in shared memory) costs ~153 cycles per K=16 instruction on B200 whatever M and N are
+// (tools/umma_rate_probe.cu, profiles/r1_umma_rate_probe.txt), so a convolution with few output channels wastes the tensor pipe
+// when the channels are the MMA's N.  This variant swaps the roles for Cout <= 128:
+//   A operand (M = 128 rows) = the packed weights (rows >= n_pad are TMA zero fill), B operand (N = 256) = 256 output pixels
+//   (two 128-pixel TMA boxes back to back), D[cout][pixel] in TMEM (2 x 256 columns).  Per instruction twice the pixels.
+// The epilogue thread owns one output channel (a TMEM lane): scale/shift/activation per thread, then a bf16 transpose through
+// shared memory so that every pixel's channels leave as contiguous 16-byte vectors (coalesced stores).
+// Tap-by-tap loading, BK = 64, LINEAR epilogue, bf16 NHWC output without residual; everything else stays on conv_igemm_kernel.
+__device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+template <int ACT>
+__device__ __forceinline__ float act_t(float v) {
+  if (ACT == 1) return fmaxf(v, 0.f);
+  if (ACT == 2) return v > 0.f ? v : 0.2f * v;
+  if (ACT == 3) return tanhf(v);
+  return v;
+}
+// One thread = one output channel: 64 pixels (4 x tcgen05.ld of 16 columns) -> act(acc*sc+sh) -> bf16 -> column `tp` of the
+// [64 px][pitch] staging tile.
+template <int ACT>
+__device__ __forceinline__ void pixn_stage(uint32_t taddr, __nv_bfloat16* tp, int pitch, float sc, float sh, bool store) {
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {  // two 16-column loads in flight per wait (register budget: 640 threads/CTA)
+    uint32_t v[2][16];
+    tmem_ld16(taddr + half * 32, v[0]);
+    tmem_ld16(taddr + half * 32 + 16, v[1]);
+    tmem_wait_ld();
+    if (store) {
+#pragma unroll
+      for (int cb = 0; cb < 2; ++cb) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          *tp = __float2bfloat16(act_t<ACT>(fmaf(__uint_as_float(v[cb][i]), sc, sh)));
+          tp += pitch;
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) conv_pixn_kernel(const __grid_constant__ ConvArgs a) {
+  constexpr uint32_t ROW = 128;              // 64 bf16 channels
+  constexpr uint32_t BOX = 128 * ROW;        // one 128-pixel box / the 128-row weight tile: 16 KB
+  constexpr uint32_t PX_BYTES = 2 * BOX;     // 256 pixels
+  constexpr uint32_t STAGE = PX_BYTES + BOX; // 48 KB
+  constexpr uint32_t SBO = 8 * ROW;
+  constexpr uint32_t NACC = 2;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  auto bar_full = [&](int s) { return base + 8u * s; };
+  auto bar_empty = [&](int s) { return base + 256u + 8u * s; };
+  auto bar_tfull = [&](int i) { return base + 1024u + 8u * i; };
+  auto bar_tempty = [&](int i) { return base + 1088u + 8u * i; };
+  const uint32_t tmem_slot = base + 1152u;
+  const uint32_t stage0 = base + 2048u;
+  const int S = a.stages;
+  const uint32_t staging0 = stage0 + (uint32_t)S * STAGE;  // kEpiWG x [64 px][store_c] bf16
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int KT = a.KH * a.KW * a.chunks;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&a.tmA);
+    tma_prefetch_desc(&a.tmB);
+  } else if (warp == 1 && lane == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(bar_full(s), 1);
+      mbar_init(bar_empty(s), 1);
+    }
+    for (int i = 0; i < (int)NACC; ++i) {
+      mbar_init(bar_tfull(i), 1);
+      mbar_init(bar_tempty(i), 128 * kEpiWG);
+    }
+    fence_mbar_init();
+  } else if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+  const int sub_shift = 7 - a.tw_log - a.th_log;  // log2(images per 128-pixel box)
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    int st = 0;
+    uint32_t ph = 0, sa = stage0;
+    for (int pair = blockIdx.x; pair < a.pairs; pair += gridDim.x) {
+      int x0[2], y0[2], n0[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        int mt = 2 * pair + h;  // a box past the last tile decodes to n0 >= Nimg: TMA zero-fills it entirely
+        const int tx = mt % a.tiles_x;
+        mt /= a.tiles_x;
+        const int ty = mt % a.tiles_y;
+        const int ti = mt / a.tiles_y;
+        x0[h] = (tx << a.tw_log) - a.off_x;
+        y0[h] = (ty << a.th_log) - a.off_y;
+        n0[h] = ti << sub_shift;
+      }
+      int tap = 0;
+      for (int ky = 0; ky < a.KH; ++ky) {
+        for (int kx = 0; kx < a.KW; ++kx, ++tap) {
+          for (int kc = 0; kc < a.chunks; ++kc) {
+            mbar_wait(bar_empty(st), ph ^ 1u);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(bar_full(st), STAGE);
+              tma_load_4d(sa, &a.tmA, bar_full(st), kc * 64, x0[0] + kx, y0[0] + ky, n0[0]);
+              tma_load_4d(sa + BOX, &a.tmA, bar_full(st), kc * 64, x0[1] + kx, y0[1] + ky, n0[1]);
+              tma_load_3d(sa + PX_BYTES, &a.tmB, bar_full(st), kc * 64, 0, tap);
+            }
+            __syncwarp();
+            sa += STAGE;
+            if (++st == S) { st = 0; ph ^= 1u; sa = stage0; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer: D[cout 128][pixel 256] += W[128][16] * X[256][16]^T
+    const uint32_t idesc = make_idesc_bf16(128, 256);
+    const uint64_t d_hi = make_smem_desc(0, SBO, 2u);
+    uint32_t acc = 0, acc_ph = 0;
+    int st = 0;
+    uint32_t ph = 0, sa = stage0;
+    for (int pair = blockIdx.x; pair < a.pairs; pair += gridDim.x) {
+      mbar_wait(bar_tempty(acc), acc_ph ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * 256u;
+      for (int k = 0; k < KT; ++k) {
+        mbar_wait(bar_full(st), ph);
+        tc_fence_after();
+        const uint64_t dw = d_hi | (uint64_t)(((sa + PX_BYTES) & 0x3FFFFu) >> 4);
+        const uint64_t dx = d_hi | (uint64_t)((sa & 0x3FFFFu) >> 4);
+        if (elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) umma_f16(d_tmem, dw + 2u * kk, dx + 2u * kk, idesc, (uint32_t)((k | kk) != 0));
+          umma_commit(bar_empty(st));
+        }
+        __syncwarp();
+        sa += STAGE;
+        if (++st == S) { st = 0; ph ^= 1u; sa = stage0; }
+      }
+      if (elect_one()) umma_commit(bar_tfull(acc));
+      __syncwarp();
+      if (++acc == NACC) { acc = 0; acc_ph ^= 1u; }
+    }
+  } else if (warp >= 4) {
+    // ===================================================== epilogue (one TMEM lane = one output channel per thread)
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int wg = (warp - 4) >> 2;    // warpgroup: pixel columns [64*wg, 64*wg+64) of the tile
+    const int r = q * 32 + lane;       // output channel, and this thread's index inside its warpgroup
+    const int sc_n = a.store_c;
+    const bool warp_active = q * 32 < sc_n;  // warp-uniform (tcgen05.ld is warp-collective)
+    const float sc = r < a.n_gemm ? (a.scale ? __ldg(a.scale + r) : 1.f) : 0.f;  // channels >= n_gemm (pad) are written as act(0)
+    const float sh = (r < a.n_gemm && a.shift) ? __ldg(a.shift + r) : 0.f;
+    __nv_bfloat16* T = reinterpret_cast<__nv_bfloat16*>(smem_raw + (staging0 - raw)) + (size_t)wg * 64 * sc_n;
+    const int vpp = sc_n >> 3;         // 16-byte vectors per pixel
+    const int nvec = 64 * vpp;
+    const int pl0 = r / vpp, c80 = r - pl0 * vpp, step_pl = 128 / vpp, step_c8 = 128 - step_pl * vpp;
+    const int tw_mask = (1 << a.tw_log) - 1, th_mask = (1 << a.th_log) - 1;
+    const int h = wg >> 1;             // which 128-pixel box of the pair this warpgroup's columns belong to
+    uint32_t acc = 0, aph = 0;
+    for (int pair = blockIdx.x; pair < a.pairs; pair += gridDim.x) {
+      int mt = 2 * pair + h;
+      const int tx = mt % a.tiles_x;
+      mt /= a.tiles_x;
+      const int ty = mt % a.tiles_y;
+      const int ti = mt / a.tiles_y;
+      mbar_wait(bar_tfull(acc), aph);
+      tc_fence_after();
+      if (warp_active) {
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256u + (uint32_t)(wg * 64);
+        __nv_bfloat16* tp = T + r;
+        switch (a.act) {  // activation selected once per tile: the 64-element loop below is straight-line code
+          case 1: pixn_stage<1>(taddr, tp, sc_n, sc, sh, r < sc_n); break;
+          case 2: pixn_stage<2>(taddr, tp, sc_n, sc, sh, r < sc_n); break;
+          case 3: pixn_stage<3>(taddr, tp, sc_n, sc, sh, r < sc_n); break;
+          default: pixn_stage<0>(taddr, tp, sc_n, sc, sh, r < sc_n); break;
+        }
+      }
+      __syncwarp();
+      tc_fence_before();
+      mbar_arrive(bar_tempty(acc));  // the accumulator is free: the MMAs of the tile after next may start
+      named_bar_sync(1 + wg, 128);   // this warpgroup's [64 px][store_c] staging tile is complete
+      {
+        // vector v = r, r+128, ... of the [64 px][vpp] tile; (pixel, chunk) advance incrementally (no divisions in the loop)
+        int pl = pl0, c8 = c80;
+        for (int v = r; v < nvec; v += 128) {
+          const int rr = ((wg & 1) << 6) + pl;  // pixel index inside the 128-pixel box
+          const int x = (tx << a.tw_log) + (rr & tw_mask);
+          const int y = (ty << a.th_log) + ((rr >> a.tw_log) & th_mask);
+          const int n = (ti << sub_shift) + (rr >> (a.tw_log + a.th_log));
+          if (x < a.Wout && y < a.Hout && n < a.Nimg) {
+            const long long pix = ((long long)n * a.Hout + y) * a.Wout + x;
+            *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) + pix * a.out_pitch + c8 * 8) =
+                *reinterpret_cast<const uint4*>(T + pl * sc_n + c8 * 8);
+          }
+          pl += step_pl;
+          c8 += step_c8;
+          if (c8 >= vpp) { c8 -= vpp; ++pl; }
+        }
+      }
+      named_bar_sync(1 + wg, 128);   // staging tile drained before the next tile overwrites it
+      if (++acc == NACC) { acc = 0; aph ^= 1u; }
+    }
+  }
+
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 
 static int log2i(int v) {
@@ -499,6 +720,19 @@ static int launch_conv(const ConvArgs& args, int grid, size_t smem, cudaStream_t
   return HRV_OK;
 }
 
+static int launch_pixn(const ConvArgs& args, int grid, size_t smem, cudaStream_t st) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(conv_pixn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (e != cudaSuccess) return set_error(HRV_ECUDA, "cudaFuncSetAttribute(conv_pixn): %s", cudaGetErrorString(e));
+    attr_done = true;
+  }
+  conv_pixn_kernel<<<grid, kThreads, smem, st>>>(args);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(HRV_ECUDA, "conv_pixn launch: %s", cudaGetErrorString(e));
+  return HRV_OK;
+}
+
 }  // namespace hrv
 
 using namespace hrv;
@@ -523,13 +757,18 @@ extern "C" int hrv_conv2d_fwd(const hrv_conv_params* p, hrv_stream stream) {
   ConvArgs a;
   memset(&a, 0, sizeof(a));
   a.Nimg = out.n; a.Hout = out.h; a.Wout = out.w;
+  // Pixel-N variant (weights as the M operand, 256 pixels as N): few output channels, plain bf16 NHWC output.
+  const char* env_pixn = getenv("HRV_CONV_PIXN");  // read per call: tests flip it to compare the two kernels on identical inputs
+  const bool pixn = !(env_pixn && env_pixn[0] == '0') && p->epi == HRV_EPI_LINEAR && p->bk == 64 && p->n_gemm <= 128 &&
+                    out.dtype == HRV_BF16 && p->out_layout == HRV_NHWC && !p->res.ptr && in.c > 32 &&
+                    ((out.c + 7) & ~7) <= out.pitch && ((out.c + 7) & ~7) <= 128;
   // Halo mode (one (16+KH-1)x(8+KW-1) box per channel chunk, taps as shifted descriptor views) whenever the image is
   // tall enough for a 16x8 single-image tile; tap-by-tap mode (tile may span images) for the tiny pyramid levels.
-  static const char* force = getenv("HRV_CONV_HALO");
+  const char* force = getenv("HRV_CONV_HALO");  // read per call (tests / A-B runs flip it)
   // Measured on B200 (tools/conv_bench.py, profiles/conv_variants_r1.txt): the halo path wins for narrow GEMMs
   // (N <= 32: 1.3-1.45x) and for the 144..208-column SPADE gamma/beta GEMMs (+5%); tap-by-tap wins for 1x1 and N=256.
   const bool halo_shape = (p->bn <= 32) || (p->bk == 16) || (p->bk == 64 && p->bn >= 144 && p->bn <= 208);
-  bool halo = out.h >= 12 && p->kh * p->kw > 1 && halo_shape;
+  bool halo = out.h >= 12 && p->kh * p->kw > 1 && halo_shape && !pixn;
   if (force && force[0] == '0') halo = false;
   if (force && force[0] == '1') halo = true;
   const int TW = halo ? 8 : pick_pow2(out.w, 128);
@@ -624,10 +863,25 @@ extern "C" int hrv_conv2d_fwd(const hrv_conv_params* p, hrv_stream stream) {
     const cuuint64_t cin_k = (cuuint64_t)a.chunks * p->bk, n_pad = (cuuint64_t)a.tiles_n * p->bn;
     cuuint64_t dims[3] = {cin_k, n_pad, (cuuint64_t)taps};
     cuuint64_t strides[2] = {cin_k * elem, n_pad * cin_k * elem};
-    cuuint32_t box[3] = {(cuuint32_t)p->bk, (cuuint32_t)p->bn, (cuuint32_t)tpb};
+    cuuint32_t box[3] = {(cuuint32_t)p->bk, (cuuint32_t)(pixn ? 128 : p->bn), (cuuint32_t)tpb};  // pixn: rows >= n_pad are zero fill
     cuuint32_t es[3] = {1, 1, 1};
     int rc = encode_tensor_map(&a.tmB, 3, const_cast<void*>(p->wpack), dims, strides, box, es, sw);
     if (rc) return rc;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (pixn) {
+    a.tiles_m = a.tiles_x * a.tiles_y * a.tiles_img;
+    a.pairs = (a.tiles_m + 1) / 2;
+    a.store_c = (out.c + 7) & ~7;
+    const uint32_t staging = (uint32_t)kEpiWG * 64u * (uint32_t)a.store_c * 2u;
+    int stages = (int)((budget - staging) / (48u * 1024u));
+    if (stages > 8) stages = 8;
+    if (stages < 2) return set_error(HRV_EINVAL, "conv(pixn): shared memory");
+    a.stages = stages;
+    const size_t smem_p = 3072 + (size_t)stages * 48 * 1024 + staging;
+    int gridp = sm_count();
+    if (a.pairs < gridp) gridp = a.pairs;
+    return launch_pixn(a, gridp, smem_p, st);
   }
   size_t smem = 3072 + (halo ? (size_t)a.stages * a.a_stage_bytes + (size_t)a.sb_stages * a.b_stage_bytes
                              : (size_t)a.stages * (128 * row_bytes + (((uint32_t)p->bn * row_bytes + 1023u) & ~1023u)));
@@ -636,7 +890,6 @@ extern "C" int hrv_conv2d_fwd(const hrv_conv_params* p, hrv_stream stream) {
   const long long total = (long long)a.tiles_n * a.tiles_x * a.tiles_y * a.tiles_img;
   int grid = sm_count();
   if (total < grid) grid = (int)total;
-  cudaStream_t st = (cudaStream_t)stream;
   switch (p->bk) {
     case 64: return launch_conv<64>(a, grid, smem, st);
     case 32: return launch_conv<32>(a, grid, smem, st);

@@ -138,6 +138,7 @@ struct ApplyArgs {
 };
 
 // grid (chunks over src pixels, N); thread = (pixel lane, channel group of src)
+template <int KIDS>  // 2: src is the half-resolution tensor behind a virtual nearest x2 (each src pixel gathers its 2x2 children); 1: same resolution
 __global__ void __launch_bounds__(256) spade_bwd_apply_kernel(ApplyArgs a) {
   extern __shared__ float shf[];  // [PL][Gs*8]
   const int n = blockIdx.y;
@@ -161,26 +162,33 @@ __global__ void __launch_bounds__(256) spade_bwd_apply_kernel(ApplyArgs a) {
       k2[i] = __ldg(a.m2 + (long long)n * a.C + c0 + i);
       dn[i] = 0.f;
     }
-    const int kids = a.shift ? 2 : 1;
+    constexpr int NK = KIDS * KIDS;
     for (long long p = p_begin + pl; p < p_end; p += a.PL) {
       const int ys = (int)(p / Ws), xs_ = (int)(p - (long long)ys * Ws);
+      // issue every load of this pixel (src + its children + their noise) before the arithmetic
+      const uint4 vx = ld16(reinterpret_cast<const __nv_bfloat16*>(a.src.ptr) + ((long long)n * HWs + p) * a.src.pitch + cs);
+      uint4 vd[NK];
+      float nz[NK];
+#pragma unroll
+      for (int k = 0; k < NK; ++k) {
+        const long long pix = ((long long)n * a.H + (ys * KIDS + k / KIDS)) * a.W + (xs_ * KIDS + k % KIDS);
+        vd[k] = ld16(reinterpret_cast<const __nv_bfloat16*>(a.dxn.ptr) + pix * a.dxn.pitch + c0);
+        nz[k] = a.noise ? __ldg(a.noise + pix) : 0.f;
+      }
       float fx[8], o[8];
-      un8(ld16(reinterpret_cast<const __nv_bfloat16*>(a.src.ptr) + ((long long)n * HWs + p) * a.src.pitch + cs), fx);
+      un8(vx, fx);
 #pragma unroll
       for (int i = 0; i < 8; ++i) o[i] = 0.f;
-      for (int dy = 0; dy < kids; ++dy) {
-        for (int dx = 0; dx < kids; ++dx) {
-          const long long pix = ((long long)n * a.H + (ys * kids + dy)) * a.W + (xs_ * kids + dx);
-          float fd[8];
-          un8(ld16(reinterpret_cast<const __nv_bfloat16*>(a.dxn.ptr) + pix * a.dxn.pitch + c0), fd);
-          const float nz = a.noise ? __ldg(a.noise + pix) : 0.f;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float xn = (fmaf(nz, nsv[i], fx[i]) - mu[i]) * rs[i];
-            const float dxs = rs[i] * (fd[i] - k1[i] - xn * k2[i]);
-            o[i] += dxs;
-            dn[i] = fmaf(dxs, nz, dn[i]);
-          }
+      for (int k = 0; k < NK; ++k) {
+        float fd[8];
+        un8(vd[k], fd);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float xn = (fmaf(nz[k], nsv[i], fx[i]) - mu[i]) * rs[i];
+          const float dxs = rs[i] * (fd[i] - k1[i] - xn * k2[i]);
+          o[i] += dxs;
+          dn[i] = fmaf(dxs, nz[k], dn[i]);
         }
       }
       *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(a.dx.ptr)) + ((long long)n * HWs + p) * a.dx.pitch + cs) = pk8(o);
@@ -262,7 +270,10 @@ extern "C" int hrv_norm_bwd_apply(const hrv_tensor* dxn, const hrv_tensor* src, 
   a.noise = noise; a.ns = noise_scale; a.mean = mean; a.rstd = rstd; a.m1 = m1; a.m2 = m2; a.dns = dns;
   unsigned gx;
   plan((long long)src->h * src->w, src->n, a.G, a.PL, a.chunk, gx);
-  spade_bwd_apply_kernel<<<dim3(gx, src->n), 256, (size_t)a.PL * a.G * 8 * sizeof(float), (cudaStream_t)stream>>>(a);
+  if (a.shift)
+    spade_bwd_apply_kernel<2><<<dim3(gx, src->n), 256, (size_t)a.PL * a.G * 8 * sizeof(float), (cudaStream_t)stream>>>(a);
+  else
+    spade_bwd_apply_kernel<1><<<dim3(gx, src->n), 256, (size_t)a.PL * a.G * 8 * sizeof(float), (cudaStream_t)stream>>>(a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(HRV_ECUDA, "norm_bwd_apply launch: %s", cudaGetErrorString(e));
   return HRV_OK;
@@ -283,16 +294,41 @@ __global__ void __launch_bounds__(256) act_bwd_bias_kernel(NView dy, NView y, NV
     long long p_end = p_begin + chunk;
     if (p_end > npix) p_end = npix;
     float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (long long p = p_begin + pl; p < p_end; p += PL) {
+    const __nv_bfloat16* dyp = reinterpret_cast<const __nv_bfloat16*>(dy.ptr) + c0;
+    const __nv_bfloat16* yp = reinterpret_cast<const __nv_bfloat16*>(y.ptr) + c0;
+    __nv_bfloat16* dvp = reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(dv.ptr)) + c0;
+    constexpr int U = 4;  // pixels per thread per iteration: 2*U independent 16-byte loads in flight (HBM latency hiding)
+    long long p = p_begin + pl;
+    for (; p + (long long)(U - 1) * PL < p_end; p += (long long)U * PL) {
+      uint4 vd[U], vy[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        vd[u] = ld16(dyp + (p + (long long)u * PL) * dy.pitch);
+        vy[u] = act != 0 ? ld16(yp + (p + (long long)u * PL) * y.pitch) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        float fd[8], fy[8], o[8];
+        un8(vd[u], fd);
+        un8(vy[u], fy);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          o[i] = act != 0 ? act_grad(fd[i], fy[i], act) : fd[i];
+          s[i] += o[i];
+        }
+        if (dv.ptr) *reinterpret_cast<uint4*>(dvp + (p + (long long)u * PL) * dv.pitch) = pk8(o);
+      }
+    }
+    for (; p < p_end; p += PL) {
       float fd[8], fy[8], o[8];
-      un8(ld16(reinterpret_cast<const __nv_bfloat16*>(dy.ptr) + p * dy.pitch + c0), fd);
-      if (act != 0) un8(ld16(reinterpret_cast<const __nv_bfloat16*>(y.ptr) + p * y.pitch + c0), fy);
+      un8(ld16(dyp + p * dy.pitch), fd);
+      if (act != 0) un8(ld16(yp + p * y.pitch), fy);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         o[i] = act != 0 ? act_grad(fd[i], fy[i], act) : fd[i];
         s[i] += o[i];
       }
-      if (dv.ptr) *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(dv.ptr)) + p * dv.pitch + c0) = pk8(o);
+      if (dv.ptr) *reinterpret_cast<uint4*>(dvp + p * dv.pitch) = pk8(o);
     }
     float* dst = shf + (long long)pl * C + c0;
 #pragma unroll

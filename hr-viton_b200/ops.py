@@ -74,8 +74,8 @@ class Act:
         """fp32 NCHW copy (API boundary / tests)."""
         out = torch.empty((self.n, self.c, self.h, self.w), dtype=torch.float32, device=self.buf.device)
         t = self.ct()
-        capi.check(capi.lib().hrv_nhwc_to_nchw(ctypes.byref(t), out.data_ptr(), _stream()), "nhwc_to_nchw")
-        LAUNCHES[0] += 1
+        with _Timed("glue", 0.0, label="nhwc_to_nchw"):
+            capi.check(capi.lib().hrv_nhwc_to_nchw(ctypes.byref(t), out.data_ptr(), _stream()), "nhwc_to_nchw")
         return out
 
 
@@ -95,8 +95,8 @@ def from_nchw(x, c_pad=None, size=None, out=None):
     if out is None:
         out = Act.empty(n, oh, ow, c, pitch=round_up(c if c_pad is None else c_pad, 8))
     t = out.ct()
-    capi.check(capi.lib().hrv_nchw_to_nhwc(x.data_ptr(), c, h, w, ctypes.byref(t), _stream()), "nchw_to_nhwc")
-    LAUNCHES[0] += 1
+    with _Timed("glue", 0.0, label="nchw_to_nhwc"):
+        capi.check(capi.lib().hrv_nchw_to_nhwc(x.data_ptr(), c, h, w, ctypes.byref(t), _stream()), "nchw_to_nhwc")
     return out
 
 
@@ -156,14 +156,15 @@ def pack_weight(w, off, cin_total=None, interleave=None, bn=None, flops_per_pixe
     inter = 2 if interleave is not None else 1
     rows, cols = (cin, cout * inter) if dgrad else (cout * inter, cin)  # GEMM N rows, K columns
     k_eff = cols if cin_total is None else cin_total
-    bk = pick_bk(k_eff)
+    # Cout <= 128: eligible for the pixel-N kernel (conv_pixn_kernel), which needs 64-channel K blocks (zero padded)
+    bk = 64 if (rows <= 128 and k_eff > 32) else pick_bk(k_eff)  # K <= 32 stays on the 32-wide blocks (padding to 64 would double the MMAs)
     cin_k = round_up(k_eff, bk)
     bn = pick_bn(rows) if bn is None else bn
     n_pad = round_up(rows, bn)
     wp = torch.empty((kh * kw, n_pad, cin_k), dtype=torch.bfloat16, device=w.device)
-    capi.check(capi.lib().hrv_pack_conv_weight(w.data_ptr(), _p(interleave), cout, cin, kh, kw, 1 if dgrad else 0, None, wp.data_ptr(),
-                                               n_pad, cin_k, _stream()), "pack_conv_weight")
-    LAUNCHES[0] += 1
+    with _Timed("glue", 0.0, label="pack_conv_weight"):
+        capi.check(capi.lib().hrv_pack_conv_weight(w.data_ptr(), _p(interleave), cout, cin, kh, kw, 1 if dgrad else 0, None, wp.data_ptr(),
+                                                   n_pad, cin_k, _stream()), "pack_conv_weight")
     fpp = 2.0 * cin * cout * inter * kh * kw if flops_per_pixel is None else flops_per_pixel
     return PackedConv(wp, kh, kw, off[0], off[1], bk, bn, rows, k_eff, fpp)
 
@@ -275,17 +276,17 @@ def instnorm_stats(x0, x0_shift, x1, h, w, noise, noise_scale, eps=1e-5):
 def instnorm_apply(x, mean, rstd, act, out=None):
     out = x if out is None else out
     tx, ty = x.ct(), out.ct()
-    capi.check(capi.lib().hrv_instnorm_apply(ctypes.byref(tx), mean.data_ptr(), rstd.data_ptr(), act, ctypes.byref(ty), _stream()),
-               "instnorm_apply")
-    LAUNCHES[0] += 1
+    with _Timed("glue", 0.0, label="instnorm_apply"):
+        capi.check(capi.lib().hrv_instnorm_apply(ctypes.byref(tx), mean.data_ptr(), rstd.data_ptr(), act, ctypes.byref(ty), _stream()),
+                   "instnorm_apply")
     return out
 
 
 def space_to_depth(x):
     out = Act.empty(x.n, (x.h + 1) // 2, (x.w + 1) // 2, 4 * round_up(x.c, 8))
     tx, ty = x.ct(), out.ct()
-    capi.check(capi.lib().hrv_space_to_depth(ctypes.byref(tx), ctypes.byref(ty), _stream()), "space_to_depth")
-    LAUNCHES[0] += 1
+    with _Timed("glue", 0.0, label="space_to_depth"):
+        capi.check(capi.lib().hrv_space_to_depth(ctypes.byref(tx), ctypes.byref(ty), _stream()), "space_to_depth")
     return out
 
 
@@ -293,32 +294,32 @@ def space_to_depth_bwd(d, n, h, w, c, pitch=None):
     """dx (n,h,w,c) of space_to_depth from the gradient d of its (n,ceil(h/2),ceil(w/2),4*c8) output."""
     dx = Act.empty(n, h, w, c, pitch=pitch)
     td, tx = d.ct(), dx.ct()
-    capi.check(capi.lib().hrv_space_to_depth_bwd(ctypes.byref(td), ctypes.byref(tx), _stream()), "space_to_depth_bwd")
-    LAUNCHES[0] += 1
+    with _Timed("glue", 0.0, label="space_to_depth_bwd"):
+        capi.check(capi.lib().hrv_space_to_depth_bwd(ctypes.byref(td), ctypes.byref(tx), _stream()), "space_to_depth_bwd")
     return dx
 
 
 def maxpool2(x):
     y = Act.empty(x.n, x.h // 2, x.w // 2, x.c, pitch=x.pitch if x.c0 == 0 else None)
     tx, ty = x.ct(), y.ct()
-    capi.check(capi.lib().hrv_maxpool2_fwd(ctypes.byref(tx), ctypes.byref(ty), _stream()), "maxpool2_fwd")
-    LAUNCHES[0] += 1
+    with _Timed("glue", 0.0, label="maxpool2_fwd"):
+        capi.check(capi.lib().hrv_maxpool2_fwd(ctypes.byref(tx), ctypes.byref(ty), _stream()), "maxpool2_fwd")
     return y
 
 
 def maxpool2_bwd(x, dy):
     dx = Act.empty(x.n, x.h, x.w, x.c, pitch=x.pitch if x.c0 == 0 else None)
     tx, tdy, tdx = x.ct(), dy.ct(), dx.ct()
-    capi.check(capi.lib().hrv_maxpool2_bwd(ctypes.byref(tx), ctypes.byref(tdy), ctypes.byref(tdx), _stream()), "maxpool2_bwd")
-    LAUNCHES[0] += 1
+    with _Timed("glue", 0.0, label="maxpool2_bwd"):
+        capi.check(capi.lib().hrv_maxpool2_bwd(ctypes.byref(tx), ctypes.byref(tdy), ctypes.byref(tdx), _stream()), "maxpool2_bwd")
     return dx
 
 
 def avgpool3s2_bwd(dy, h, w):
     dx = Act.empty(dy.n, h, w, dy.c, pitch=dy.pitch if dy.c0 == 0 else None)
     tdy, tdx = dy.ct(), dx.ct()
-    capi.check(capi.lib().hrv_avgpool3s2_bwd(ctypes.byref(tdy), ctypes.byref(tdx), _stream()), "avgpool3s2_bwd")
-    LAUNCHES[0] += 1
+    with _Timed("glue", 0.0, label="avgpool3s2_bwd"):
+        capi.check(capi.lib().hrv_avgpool3s2_bwd(ctypes.byref(tdy), ctypes.byref(tdx), _stream()), "avgpool3s2_bwd")
     return dx
 
 
@@ -329,8 +330,8 @@ def im2col(x, kh, kw, pad, k_pad=None):
         k_pad = round_up(k, 64) if k > 32 else (32 if k > 16 else 16)
     out = Act.empty(x.n, x.h, x.w, k_pad)
     tx, to = x.ct(), out.ct()
-    capi.check(capi.lib().hrv_im2col(ctypes.byref(tx), ctypes.byref(to), kh, kw, pad, _stream()), "im2col")
-    LAUNCHES[0] += 1
+    with _Timed("glue", 0.0, label="im2col"):
+        capi.check(capi.lib().hrv_im2col(ctypes.byref(tx), ctypes.byref(to), kh, kw, pad, _stream()), "im2col")
     return out
 
 
@@ -338,8 +339,8 @@ def l1_sum(a, b):
     """sum |a - b| as a 1-element fp64 cuda tensor."""
     out = torch.empty(1, dtype=torch.float64, device=a.buf.device)
     ta, tb = a.ct(), b.ct()
-    capi.check(capi.lib().hrv_l1_sum(ctypes.byref(ta), ctypes.byref(tb), out.data_ptr(), _stream()), "l1_sum")
-    LAUNCHES[0] += 1
+    with _Timed("glue", 0.0, label="l1_sum"):
+        capi.check(capi.lib().hrv_l1_sum(ctypes.byref(ta), ctypes.byref(tb), out.data_ptr(), _stream()), "l1_sum")
     return out
 
 
@@ -347,8 +348,8 @@ def l1_bwd(a, b, gscale):
     """da = sign(a - b) * gscale (gscale: 1-element fp32 cuda tensor)."""
     da = Act.empty(a.n, a.h, a.w, a.c, pitch=a.pitch if a.c0 == 0 else None)
     ta, tb, td = a.ct(), b.ct(), da.ct()
-    capi.check(capi.lib().hrv_l1_bwd(ctypes.byref(ta), ctypes.byref(tb), gscale.data_ptr(), ctypes.byref(td), _stream()), "l1_bwd")
-    LAUNCHES[0] += 1
+    with _Timed("glue", 0.0, label="l1_bwd"):
+        capi.check(capi.lib().hrv_l1_bwd(ctypes.byref(ta), ctypes.byref(tb), gscale.data_ptr(), ctypes.byref(td), _stream()), "l1_bwd")
     return da
 
 
@@ -361,25 +362,25 @@ def parse_blur_argmax(seg, size, group_of=None, groups=0, want_idx=True):
     idx = torch.empty((n, 1, H, W), dtype=torch.int64, device=seg.device) if want_idx else None
     onehot = torch.empty((n, groups, H, W), dtype=torch.float32, device=seg.device) if group_of is not None else None
     garr = (ctypes.c_int32 * c)(*group_of) if group_of is not None else None
-    capi.check(capi.lib().hrv_parse_blur_argmax(seg.data_ptr(), n, c, h, w, H, W, garr, groups, _p(idx), _p(onehot), _stream()),
-               "parse_blur_argmax")
-    LAUNCHES[0] += 1
+    with _Timed("glue", 0.0, label="parse_blur_argmax"):
+        capi.check(capi.lib().hrv_parse_blur_argmax(seg.data_ptr(), n, c, h, w, H, W, garr, groups, _p(idx), _p(onehot), _stream()),
+                   "parse_blur_argmax")
     return idx, onehot
 
 
 def avgpool3s2(x):
     out = Act.empty(x.n, (x.h - 1) // 2 + 1, (x.w - 1) // 2 + 1, x.c, pitch=x.pitch if x.c0 == 0 else None)
     tx, ty = x.ct(), out.ct()
-    capi.check(capi.lib().hrv_avgpool3s2(ctypes.byref(tx), ctypes.byref(ty), _stream()), "avgpool3s2")
-    LAUNCHES[0] += 1
+    with _Timed("glue", 0.0, label="avgpool3s2"):
+        capi.check(capi.lib().hrv_avgpool3s2(ctypes.byref(tx), ctypes.byref(ty), _stream()), "avgpool3s2")
     return out
 
 
 def bilinear_up2_add(a, b, out):
     ta, to = a.ct(), out.ct()
     tb = b.ct() if b is not None else _NULL
-    capi.check(capi.lib().hrv_bilinear_up2_add(ctypes.byref(ta), ctypes.byref(tb), ctypes.byref(to), _stream()), "bilinear_up2_add")
-    LAUNCHES[0] += 1
+    with _Timed("glue", 0.0, label="bilinear_up2_add"):
+        capi.check(capi.lib().hrv_bilinear_up2_add(ctypes.byref(ta), ctypes.byref(tb), ctypes.byref(to), _stream()), "bilinear_up2_add")
     return out
 
 
@@ -404,9 +405,9 @@ def flow_warp(flow_lo, src, dst, want_flow_up=True, want_idx=False):
     flow_up = torch.empty((n, H, W, 2), dtype=torch.float32, device=dev) if want_flow_up else None
     idx = torch.empty((n, H, W, 2), dtype=torch.int32, device=dev) if want_idx else None
     ts, td = src.ct(), dst.ct()
-    capi.check(capi.lib().hrv_flow_warp(flow_lo.data_ptr(), linspace_table(W, dev).data_ptr(), linspace_table(H, dev).data_ptr(),
-                                        ctypes.byref(ts), ctypes.byref(td), _p(flow_up), _p(idx), _stream()), "flow_warp")
-    LAUNCHES[0] += 1
+    with _Timed("glue", 0.0, label="flow_warp"):
+        capi.check(capi.lib().hrv_flow_warp(flow_lo.data_ptr(), linspace_table(W, dev).data_ptr(), linspace_table(H, dev).data_ptr(),
+                                            ctypes.byref(ts), ctypes.byref(td), _p(flow_up), _p(idx), _stream()), "flow_warp")
     return flow_up, idx
 
 

@@ -183,9 +183,12 @@ class SPADEResBlock(nn.Module):
             norms = ([self.norm_s] if self.learned_shortcut else []) + [self.norm_0, self.norm_1]
             # one conv_shared GEMM for all norms of the block: N = 128 * len(norms), same seg operand read once
             wsh = torch.cat([m.conv_shared[0].weight.detach() for m in norms], 0)
-            if 9 * wsh.shape[1] <= 64:  # few-channel label map: column (im2col) form, one K=64 block instead of nine K=16 taps
+            if 9 * wsh.shape[1] <= 64:
+                # few-channel label map: column (im2col) form, one K=64 block instead of nine K=16 taps; one 128-channel GEMM per
+                # norm (<= 128 output channels keeps each on the pixel-N kernel) writing its slice of the shared actv buffer
                 from .autograd_g import im2col_weight
-                shared = ops.pack_weight(im2col_weight(wsh, 64), (0, 0), flops_per_pixel=2.0 * wsh.shape[0] * wsh.shape[1] * 9)
+                shared = [ops.pack_weight(im2col_weight(m.conv_shared[0].weight.detach(), 64), (0, 0),
+                                          flops_per_pixel=2.0 * m.conv_shared[0].weight.shape[0] * wsh.shape[1] * 9) for m in norms]
             else:
                 shared = ops.pack_weight(wsh, (1, 1))
             c = {"shared": shared,
@@ -214,8 +217,16 @@ class SPADEResBlock(nn.Module):
         noise_fn(n,h,w) -> fp32 (n,h,w) cuda; draw order norm_s, norm_0, norm_1 (network_generator.py:157-171)."""
         p = self._packed()
         n, h, w = seg.n, seg.h, seg.w
-        src = ops.im2col(seg, 3, 3, 1, k_pad=64) if p["shared"].kh == 1 else seg
-        actv = ops.conv2d(src, p["shared"], Act.empty(n, h, w, p["shared"].n_gemm), act=ACT_RELU, shift=p["shared_b"])
+        if isinstance(p["shared"], list):
+            cols = ops.im2col(seg, 3, 3, 1, k_pad=64)
+            nsh = sum(pw.n_gemm for pw in p["shared"])
+            actv = Act.empty(n, h, w, nsh)
+            c0 = 0
+            for pw in p["shared"]:
+                ops.conv2d(cols, pw, actv.slice(c0, pw.n_gemm), act=ACT_RELU, shift=p["shared_b"][c0:c0 + pw.n_gemm])
+                c0 += pw.n_gemm
+        else:
+            actv = ops.conv2d(seg, p["shared"], Act.empty(n, h, w, p["shared"].n_gemm), act=ACT_RELU, shift=p["shared_b"])
         k = 0
         if self.learned_shortcut:
             hs = self._spade(p["ns"], actv.slice(0, 128), x0, x0_shift, x1, noise_fn(n, h, w), ACT_NONE)

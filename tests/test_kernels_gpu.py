@@ -381,3 +381,50 @@ def test_l1_sum_and_bwd():
     da = ops.l1_bwd(A, B, gs).buf.float().cpu().permute(0, 3, 1, 2)
     want = (a.grad * 0.5).to(torch.bfloat16).float()
     assert torch.equal(da, want)
+
+
+PIXN_CASES = [  # n, cin, cout, h, w, k, pad, act, bias, scale, out_pitch
+    (2, 80, 32, 40, 24, 3, 1, 2, True, False, None),     # SW128 K padding 80 -> 128, partial tiles
+    (1, 48, 32, 64, 48, 3, 1, 0, True, True, None),
+    (3, 160, 128, 17, 13, 3, 1, 1, True, False, None),   # odd extents, odd number of 128-pixel boxes
+    (8, 64, 128, 8, 6, 1, 0, 1, True, False, None),      # several images per box (tiny pyramid level)
+    (2, 64, 3, 32, 24, 3, 1, 3, True, False, None),      # 3 output channels (pad channels written as zero)
+    (1, 256, 128, 33, 25, 2, 1, 2, False, False, None),  # the 2x2/pad-1 form of the stride-2 convolutions (extent H+1)
+    (2, 40, 72, 20, 20, 4, 2, 0, True, False, None),     # 4x4 / pad 2 (PatchGAN stride-1 layers), cout not a multiple of 16
+    (1, 128, 64, 48, 40, 3, 1, 0, False, False, 96),     # output into a wider buffer (channel slice of a concat buffer)
+]
+
+
+@pytest.mark.parametrize("case", PIXN_CASES)
+def test_conv_pixn_matches_classic_kernel(case):
+    """The pixel-N kernel (weights as the MMA's M operand, 256 pixels as N, transposed epilogue) accumulates the same products in
+    the same K order as the classic kernel: outputs must be bit-identical.  HRV_CONV_PIXN=0 selects the classic kernel."""
+    n, cin, cout, h, w, k, pad, act, bias, scale, out_pitch = case
+    x = Act(_to_buf(bf16r(synth.normalish((n, cin, h, w), 11, "x"))), c=cin)
+    wt = synth.normalish((cout, cin, k, k), 11, "w", (1.0 / (cin * k * k)) ** 0.5).to(DEV)
+    b = synth.normalish((cout,), 11, "b", 0.1).to(DEV) if bias else None
+    sc = synth.uniform((cout,), 11, "s", 0.5, 1.5).to(DEV) if scale else None
+    pw = ops.pack_weight(wt, (pad, pad))
+    assert pw.bk == 64
+    oh, ow = h + 2 * pad - k + 1, w + 2 * pad - k + 1
+    outs = []
+    try:
+        os.environ["HRV_CONV_HALO"] = "0"  # classic kernel in tap-by-tap order: the same fp32 accumulation order as the pixel-N kernel
+        for flag in ("0", "1"):
+            os.environ["HRV_CONV_PIXN"] = flag
+            o = Act(torch.zeros((n, oh, ow, out_pitch or ops.round_up(cout, 8)), dtype=torch.bfloat16, device=DEV), c=cout)
+            ops.conv2d(x, pw, o, act=act, scale=sc, shift=b)
+            torch.cuda.synchronize()
+            outs.append(o.buf.clone())
+    finally:
+        os.environ.pop("HRV_CONV_PIXN", None)
+        os.environ.pop("HRV_CONV_HALO", None)
+    bad = outs[0] != outs[1]
+    assert not bool(bad.any()), "%d mismatching elements, first at %s" % (int(bad.sum()), bad.nonzero()[:4].tolist())
+    ref = F.conv2d(x.buf[..., :cin].permute(0, 3, 1, 2).float().cpu(), bf16r(wt.cpu()), None, padding=pad)
+    if sc is not None:
+        ref = ref * sc.cpu()[None, :, None, None]
+    if b is not None:
+        ref = ref + b.cpu()[None, :, None, None]
+    ref = {0: lambda t: t, 1: torch.relu, 2: lambda t: F.leaky_relu(t, 0.2), 3: torch.tanh}[act](ref)
+    assert rel_err(outs[1][..., :cout].permute(0, 3, 1, 2), ref) < 1e-2
