@@ -427,9 +427,10 @@ def main():
     conv_ms = agg.get("conv", [0, 0, 0])[1] + agg.get("conv_spade", [0, 0, 0])[1]
     conv_launches = agg.get("conv", [0, 0, 0])[2] + agg.get("conv_spade", [0, 0, 0])[2]
     achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
-    roofline = {"kernel": "conv_igemm_kernel (tcgen05 implicit-GEMM conv, all %d launches of one step)" % conv_launches,
+    roofline = {"kernel": "conv_igemm_kernel + conv_pixn_kernel (tcgen05 implicit-GEMM convolution, all %d launches of one step)" % conv_launches,
                 "bound": "tensor", "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["tf_sustained"], "traffic": conv_traffic(), "peak_source": peaks["src"] + " (bf16 sustained)",
+                "frac": achieved / peaks["tf_sustained"],
+                "traffic": conv_traffic() if (train and not stage1 and B == 8) else None,  # the ncu pass was taken on the default workload "peak_source": peaks["src"] + " (bf16 sustained)",
                 "avg_launch_ms": conv_ms / max(1, conv_launches), "algorithmic_gflop_per_launch": conv_flops / 1e9 / max(1, conv_launches)}
     total_prof_ms = sum(a[1] for a in agg.values())
     breakdown = {k: {"ms": round(a[1], 3), "launches": a[2], "share": round(a[1] / total_prof_ms, 4)} for k, a in agg.items()}

@@ -90,3 +90,51 @@ def test_s2d_weight_equivalence_on_cpu():
         s = xp.reshape(n, c, hh // 2, 2, ww // 2, 2).permute(0, 3, 5, 1, 2, 4).reshape(n, 4 * c, hh // 2, ww // 2)  # channel (py*2+px)*c8+ci
         got = F.conv2d(s, ops.s2d_weight(wt, pad), stride=1, padding=1)[:, :, :ref.shape[2], :ref.shape[3]]
         assert torch.allclose(got, ref, atol=1e-4), (k, pad, h, w)
+
+
+def test_im2col_weight_equivalence_on_cpu():
+    """autograd_g.im2col_weight: a 3x3 convolution over a few-channel map == a 1x1 convolution over the tap-major columns that
+    hrv_im2col produces (column j = tap*C + ci, zero padded to 64) — checked with F.unfold as the column builder."""
+    import torch.nn.functional as F
+    from hrviton_b200 import autograd_g
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 7, 9, 6, generator=g)
+    w = torch.randn(12, 7, 3, 3, generator=g, requires_grad=True)
+    cols = F.unfold(x, 3, padding=1).reshape(2, 7, 9, 9 * 6).permute(0, 2, 1, 3).reshape(2, 63, 9, 6)  # tap-major
+    cols = F.pad(cols, (0, 0, 0, 0, 0, 1))
+    wc = autograd_g.im2col_weight(w, 64)
+    assert wc.shape == (12, 64, 1, 1)
+    out = F.conv2d(cols, wc)
+    ref = F.conv2d(x, w, padding=1)
+    assert float((out - ref).abs().max()) < 1e-5
+    # the index shuffle is differentiable: the 1x1 weight gradient maps back onto the 3x3 parameter
+    out.square().sum().backward()
+    g1 = w.grad.clone()
+    w.grad = None
+    ref.square().sum().backward()
+    assert float((g1 - w.grad).abs().max()) < 1e-3 * float(w.grad.abs().max())
+
+
+def test_label_regrouping_table():
+    """train_step.GROUP_OF_13 is the inverse of the 7-group label table (train_generator.py:261-269): every class in exactly one group."""
+    from hrviton_b200 import train_step
+    assert len(train_step.GROUP_OF_13) == 13
+    for k, grp in enumerate(train_step.GROUP_OF_13):
+        assert k in train_step.LABELS7[grp]
+    assert sorted(sum(train_step.LABELS7, [])) == list(range(13))
+
+
+def test_gaussian_blur_restatement_is_normalised_and_separable():
+    """gaussian_blur_15_3 (the checker of the fused parse kernel): constant image -> constant away from the zero-padded border,
+    and equal to the explicit 15x15 outer-product kernel."""
+    import torch.nn.functional as F
+    from hrviton_b200 import train_step
+    x = torch.ones(1, 2, 40, 40)
+    y = train_step.gaussian_blur_15_3(x)
+    assert float((y[..., 10:30, 10:30] - 1).abs().max()) < 1e-5
+    k = torch.arange(15, dtype=torch.float32) - 7
+    g = torch.exp(-(k * k) / 18.0)
+    g = g / g.sum()
+    z = torch.randn(1, 1, 32, 32, generator=torch.Generator().manual_seed(1))
+    ref = F.conv2d(z, torch.outer(g, g)[None, None], padding=7)
+    assert float((train_step.gaussian_blur_15_3(z) - ref).abs().max()) < 1e-5
