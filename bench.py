@@ -234,6 +234,9 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    # NCCL prints its version banner on STDOUT at NCCL_DEBUG=VERSION (the image's default): keep stdout to the one JSON line
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
     import torch
     import torch.distributed as dist
 
