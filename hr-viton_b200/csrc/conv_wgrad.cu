@@ -9,6 +9,8 @@
 // Grid = (co tiles) x (ci tiles) x KH x splits; each CTA streams its share of the (n, y, x-segment) chunks and finally adds its
 // fp32 partial tile into dW with red.global.add (dW is zeroed by the caller).
 // Replaces the weight-gradient half of nn.Conv2d's backward (networks.py / network_generator.py convolutions, stage-2 training).
+#include <stdlib.h>
+
 #include "hrv_host.h"
 #include "hrv_ptx.cuh"
 
@@ -171,9 +173,25 @@ extern "C" int hrv_conv2d_wgrad(const hrv_tensor* x, const hrv_tensor* dy, int32
   a.dw = dw;
   const int chunks = a.Nimg * a.OH * a.xsegs;
   const int tiles = a.m_tiles * a.n_tiles * kh;
-  int splits = (2 * sm_count() + tiles - 1) / tiles;  // ~2 waves of CTAs
-  if (splits > chunks) splits = chunks;
-  if (splits < 1) splits = 1;
+  // Split-K factor: one CTA per SM is resident (512 TMEM columns each), CTAs of one launch take equal time, so the launch costs
+  // waves * (chunks per CTA + fixed prologue/epilogue) with waves = ceil(grid / SMs).  Pick the split that minimises it — a grid
+  // that spills a few CTAs into an extra wave (e.g. 300 CTAs on 148 SMs) costs a whole wave.
+  const int sms = sm_count();
+  int splits = 1;
+  {
+    const long long kFixed = 16;  // prologue + TMEM read-out + red.global epilogue, in units of one 64-pixel chunk step
+    long long best = -1;
+    int smax = 8 * sms / tiles + 1;
+    if (smax > chunks) smax = chunks;
+    if (smax < 1) smax = 1;
+    for (int sp = 1; sp <= smax; ++sp) {
+      const long long waves = ((long long)tiles * sp + sms - 1) / sms;
+      const long long cost = waves * ((chunks + sp - 1) / sp + kFixed);
+      if (best < 0 || cost < best) { best = cost; splits = sp; }
+    }
+    const char* env = getenv("HRV_WGRAD_SPLITS");  // A/B runs
+    if (env && atoi(env) > 0) splits = atoi(env) < chunks ? atoi(env) : chunks;
+  }
   a.splits = splits;
   const uint32_t stage_bytes = 2u * kPX * 128u + ((((uint32_t)(kPX + kw - 1) * 128u + 1023u) & ~1023u) * (uint32_t)(a.BN / 64));
   int stages = (int)((200u * 1024u) / stage_bytes);

@@ -56,6 +56,10 @@ typedef struct hrv_tensor {
  *                       * (1 + acc[2c] + shift[2c]) + (acc[2c+1] + shift[2c+1]);  out[c] = act(v)
  *                   x0 may be half resolution (x0_shift=1: nearest x2 up-sampling folded into the index,
  *                   network_generator.py:203,226-242); x1 supplies channels [x0.c, x0.c+x1.c) (the torch.cat).
+ *
+ * Kernel selection (same results bit for bit within one K order): LINEAR, bk = 64, n_gemm <= 128, bf16 NHWC output, no residual and
+ * in.c > 32 run on the pixel-N kernel (weights as the MMA's M operand, 256 pixels as N); everything else on the classic kernel
+ * (pixels as M), tap-by-tap or halo mainloop.  Environment switches for A/B runs, read per call: HRV_CONV_PIXN=0, HRV_CONV_HALO=0|1.
  */
 typedef struct hrv_conv_params {
   hrv_tensor in;
