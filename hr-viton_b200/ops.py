@@ -8,6 +8,7 @@ from . import capi
 from .capi import ACT_LRELU, ACT_NONE, ACT_RELU, ACT_TANH, BF16, F32  # noqa: F401
 
 LAUNCHES = [0]  # count of kernel launches issued through the C-ABI (bench.py reads this for `gpu_launches`)
+PARAM_GEN = [0]  # generation of the parameter values: part of every derived-weight cache key (spade._param_key)
 PROFILE = None  # bench.py sets this to a list; every C-ABI call then appends (kind, work, start_event, end_event)
 
 

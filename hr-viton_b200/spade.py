@@ -21,7 +21,15 @@ def _need_cuda(t, who):
 
 
 def _param_key(module):
-    return tuple((p.data_ptr(), p._version) for p in list(module.parameters()) + list(module.buffers()))
+    """Cache key of the derived (packed bf16 / folded BatchNorm) copies of a module's parameters and buffers.  `_version` catches
+    eager in-place updates (optimizer.step, load_state_dict); ops.PARAM_GEN catches what `_version` cannot see — CUDA-graph replays
+    of a captured optimiser step and `.data` edits — and is bumped by the trainers' replay()/step() and by `invalidate_caches()`."""
+    return (ops.PARAM_GEN[0],) + tuple((p.data_ptr(), p._version) for p in list(module.parameters()) + list(module.buffers()))
+
+
+def invalidate_caches():
+    """Forget every packed-weight / folded-BatchNorm cache (call after editing parameters behind autograd's back)."""
+    ops.PARAM_GEN[0] += 1
 
 
 class BaseNetwork(nn.Module):
@@ -291,7 +299,7 @@ class SPADEGenerator(BaseNetwork):
 
     def _pyramid_packed(self):
         convs = [getattr(self, "conv_%d" % i) for i in range(8)] + [self.conv_img]
-        key = tuple((c.weight.data_ptr(), c.weight._version, c.bias._version) for c in convs)
+        key = (ops.PARAM_GEN[0],) + tuple((c.weight.data_ptr(), c.weight._version, c.bias._version) for c in convs)
         if key != self._pyr_key:
             self._pyr = [(ops.pack_weight(c.weight.detach(), (1, 1)), c.bias.detach().float().contiguous()) for c in convs]
             self._pyr_key = key

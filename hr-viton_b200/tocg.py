@@ -64,8 +64,6 @@ class ResBlock(nn.Module):
     def _packed(self, cin_total):
         key = (_param_key(self), cin_total)
         if key != self._cache_key:
-            if self.training:
-                raise NotImplementedError("train-mode BatchNorm (batch statistics) is not implemented yet: call .eval()")
             c = {}
             if self.kind == "down":
                 w = self.scale.weight.detach()
@@ -104,6 +102,12 @@ class ResBlock(nn.Module):
 
     def forward(self, x):
         _need_cuda(x, "ResBlock")
+        if self.training:
+            # train-mode BatchNorm (batch statistics, running-stat update) lives in the autograd path (networks.py:188-198)
+            from . import autograd_tocg
+            from .autograd_g import FromNCHW
+            y = autograd_tocg._resblock(self, FromNCHW.apply(x.float(), None, None))
+            return y[..., :self.out_nc].permute(0, 3, 1, 2).float()
         with torch.no_grad():
             return self.run(ops.from_nchw(x.float())).to_nchw()
 
@@ -169,8 +173,14 @@ class ConditionGenerator(nn.Module):
         _need_cuda(input1, "ConditionGenerator")
         if self.warp_feature != "T1" or self.out_layer_opt != "relu":
             raise NotImplementedError("kernels cover warp_feature='T1', out_layer='relu' (the reference's configuration)")
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
-            raise NotImplementedError("ConditionGenerator training (stage 1) backward is not implemented yet")
+        if self.training:
+            # train mode = batch-statistics BatchNorm (+ running-stat updates) exactly as nn.BatchNorm2d in the reference
+            # (train_condition.py:158 calls tocg(input1, input2) in train mode); with grad enabled it also carries the autograd graph
+            from . import autograd_tocg
+            return autograd_tocg.tocg_forward_train(self, input1, input2)
+        if torch.is_grad_enabled() and (input1.requires_grad or input2.requires_grad):
+            raise NotImplementedError("eval-mode ConditionGenerator is inference only (folded BatchNorm): no gradient w.r.t. its inputs; "
+                                      "call .train() for the differentiable path or wrap the call in torch.no_grad()")
         with torch.no_grad():
             return self._forward_impl(input1.float().contiguous(), input2.float().contiguous())
 
@@ -360,8 +370,10 @@ class MultiscaleDiscriminator(nn.Module):
 
     def forward(self, input):
         _need_cuda(input, "MultiscaleDiscriminator")
-        if torch.is_grad_enabled() and (input.requires_grad or any(p.requires_grad for p in self.parameters())) and self.training:
-            raise NotImplementedError("stage-1 discriminator backward is not implemented yet")
+        if torch.is_grad_enabled() and (input.requires_grad or any(p.requires_grad for p in self.parameters())) and not self.getIntermFeat:
+            # differentiable path (train_condition.py:208-232: D(fake) back-propagates into tocg, D(real/fake.detach()) into D)
+            from . import autograd_tocg
+            return autograd_tocg.tocg_discriminator_forward_train(self, input)
         with torch.no_grad():
             a = ops.from_nchw(input.float())
             if self.Ddownx2:

@@ -97,6 +97,8 @@ class _GraphMixin:
             for k, v in batch.items():
                 self._static[k].copy_(v, non_blocking=True)
         self._graph.replay()
+        from . import ops
+        ops.PARAM_GEN[0] += 1  # the replayed optimiser step changed parameters without touching tensor._version: derived caches are stale
         return self._graph_out
 
 

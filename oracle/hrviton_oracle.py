@@ -145,8 +145,45 @@ def np_spectral_sigma(w_orig, u, v):
 # --------------------------------------------------------------------------------------
 
 
+# --- storage-rounding model ("what does 16-bit activation storage cost the fp32 algorithm itself?") -------------------------------
+# With storage_rounding(torch.bfloat16 | torch.float16) active, every convolution of the restatement rounds its input
+# activations, its weights and its output to that type (and, through autograd, the gradients flowing back through the same
+# points) while all arithmetic stays fp32.  This is the *floor* any implementation that keeps activations in a 16-bit type
+# must sit on; tests assert that the CUDA kernels deviate from the fp32 goldens by no more than 1.1x what this model does.
+_ROUND = [None, True]  # [dtype | None, also round conv outputs]
+
+
+class storage_rounding:
+    def __init__(self, dtype, outputs=True):
+        self.new = [dtype, outputs]
+
+    def __enter__(self):
+        self.old = list(_ROUND)
+        _ROUND[:] = self.new
+        return self
+
+    def __exit__(self, *exc):
+        _ROUND[:] = self.old
+        return False
+
+
+def _q(t):
+    if _ROUND[0] is None or t is None:
+        return t
+    return t.to(_ROUND[0]).to(torch.float32)
+
+
+def _qo(t):
+    return _q(t) if _ROUND[1] else t
+
+
+def conv2d_q(x, w, b=None, stride=1, padding=0):
+    """F.conv2d under the storage-rounding model (identity when no rounding is active)."""
+    return _qo(F.conv2d(_q(x), _q(w), b, stride=stride, padding=padding))
+
+
 def _conv(sd, name, x, stride=1, padding=0):
-    return F.conv2d(x, sd[name + ".weight"], sd.get(name + ".bias"), stride=stride, padding=padding)
+    return conv2d_q(x, sd[name + ".weight"], sd.get(name + ".bias"), stride=stride, padding=padding)
 
 
 def _bn_eval(sd, name, x, eps=1e-5):
@@ -261,13 +298,13 @@ def spade_resblock(sd, p, x, seg_full, noise_fn):
     learned = (p + ".conv_s.weight_orig") in sd
     if learned:
         hs = spade_norm(sd, p + ".norm_s", x, seg, noise_fn(n, h, w))
-        x_s = F.conv2d(hs, spectral_weight(sd, p + ".conv_s"))
+        x_s = conv2d_q(hs, spectral_weight(sd, p + ".conv_s"))
     else:
         x_s = x
     h0 = F.leaky_relu(spade_norm(sd, p + ".norm_0", x, seg, noise_fn(n, h, w)), 0.2)
-    dx = F.conv2d(h0, spectral_weight(sd, p + ".conv_0"), sd[p + ".conv_0.bias"], padding=1)
+    dx = conv2d_q(h0, spectral_weight(sd, p + ".conv_0"), sd[p + ".conv_0.bias"], padding=1)
     h1 = F.leaky_relu(spade_norm(sd, p + ".norm_1", dx, seg, noise_fn(n, h, w)), 0.2)
-    dx = F.conv2d(h1, spectral_weight(sd, p + ".conv_1"), sd[p + ".conv_1.bias"], padding=1)
+    dx = conv2d_q(h1, spectral_weight(sd, p + ".conv_1"), sd[p + ".conv_1.bias"], padding=1)
     return x_s + dx
 
 
@@ -299,7 +336,7 @@ def gen_d_forward(sd, inp, num_d=2, n_layers=3):
         feats.append(h)
         for n in range(1, n_layers):
             q = p + ".model%d.0.0" % n
-            h = F.conv2d(h, spectral_weight(sd, q), None, stride=2, padding=2)
+            h = conv2d_q(h, spectral_weight(sd, q), None, stride=2, padding=2)
             h = F.leaky_relu(_inorm(h), 0.2)
             feats.append(h)
         feats.append(_conv(sd, p + ".model%d.0" % n_layers, h, stride=1, padding=2))
@@ -317,7 +354,7 @@ def tocg_d_forward(sd, inp, num_d=2, n_layers=3, ddownx2=True):
         for j, ci in enumerate(idx):
             w = sd["%s.%d.weight" % (prefix, ci)]
             stride = 2 if j < n_layers else 1
-            x = F.conv2d(x, w, sd["%s.%d.bias" % (prefix, ci)], stride=stride, padding=2)
+            x = conv2d_q(x, w, sd["%s.%d.bias" % (prefix, ci)], stride=stride, padding=2)
             if ci == last:
                 break
             if j > 0:

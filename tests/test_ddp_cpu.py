@@ -59,6 +59,52 @@ def test_bucket_reducer_two_ranks():
         assert torch.allclose(r0[i], want, atol=1e-6) and torch.allclose(r1[i], want, atol=1e-6)
 
 
+def _worker_auto(rank, world, port, out):
+    """The reference loop's pattern (train_generator.py:314-322): wrap, forward, loss.backward(), optimizer.step() — no explicit
+    reduce call.  Replicas must start identical (broadcast at wrap time) and stay identical."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["WORLD_SIZE"] = str(world)
+    os.environ["RANK"] = str(rank)
+    torch.manual_seed(100 + rank)  # different initial weights per rank on purpose
+    net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.BatchNorm1d(5), torch.nn.Linear(5, 3))
+    dead = torch.nn.Linear(2, 2)
+    net.add_module("dead", dead)
+    net.forward = lambda x: net[2](net[1](net[0](x)))
+    wrapped = ddp.DataParallelWithCallback(net, device_ids=[0])  # initialises gloo from the environment, broadcasts rank 0's state
+    w0 = [p.detach().clone() for p in net.parameters()]
+    b0 = [b.detach().clone() for b in net.buffers()]
+    opt = torch.optim.SGD([p for p in net.parameters()], lr=0.1)
+    xs = [torch.randn(4, 6, generator=torch.Generator().manual_seed(7 + 10 * it + rank)) for it in range(3)]
+    locals_, launched = [], []
+    for it in range(3):
+        opt.zero_grad()  # set_to_none=True, like the reference's optimizer.zero_grad() on a modern torch
+        loss = wrapped(xs[it]).pow(2).sum()
+        loss.backward()
+        launched.append(wrapped._reducer.launched)
+        opt.step()
+    out[rank] = (w0, b0, [p.detach().clone() for p in net.parameters()], [p.grad.clone() if p.grad is not None else None for p in net.parameters()],
+                 launched)
+    dist.destroy_process_group()
+
+
+def test_wrapper_synchronises_without_explicit_reduce():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker_auto, args=(world, _free_port(), out), nprocs=world, join=True)
+    (w0a, b0a, wa, ga, la), (w0b, b0b, wb, gb, lb) = out[0], out[1]
+    for x, y in zip(w0a + b0a, w0b + b0b):
+        assert torch.equal(x, y)  # broadcast at wrap time
+    for x, y in zip(wa, wb):
+        assert torch.equal(x, y)  # identical after 3 optimiser steps: gradients were averaged automatically
+    assert any(not torch.equal(x, y) for x, y in zip(w0a, wa))  # and training actually moved them
+    for x, y in zip(ga, gb):
+        assert (x is None) == (y is None) and (x is None or torch.equal(x, y))
+    assert ga[-1] is None  # the dead branch got no gradient and was skipped
+    assert la == lb and all(n >= 1 for n in la)
+
+
 def test_wrapper_keeps_module_attribute():
     m = torch.nn.Linear(2, 2)
     w = ddp.DataParallelWithCallback(m, device_ids=[0])
