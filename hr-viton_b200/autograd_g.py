@@ -93,8 +93,8 @@ class ConvFn(torch.autograd.Function):
             dv = _act_grad(dy, y, act)
             if has_bias and ctx.needs_input_grad[2]:
                 db = dv.sum((0, 1, 2), dtype=torch.float32)
-            dv_buf = torch.zeros(dv.shape[:3] + (ops.round_up(cout, 8),), dtype=torch.bfloat16, device=dv.device)
-            dv_buf[..., :cout] = dv.to(torch.bfloat16)
+            dv_buf = torch.zeros(dv.shape[:3] + (ops.round_up(cout, 8),), dtype=x_buf.dtype, device=dv.device)
+            dv_buf[..., :cout] = dv.to(x_buf.dtype)
         else:  # one fused pass: activation backward + bias gradient
             want_b = has_bias and ctx.needs_input_grad[2]
             dva, db = ops.act_bwd_bias(Act(dy.contiguous(), c=cout), Act(y, c=cout) if y is not None else None, act, want_bias=want_b)

@@ -6,7 +6,7 @@ import os
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG, "libhrviton_sm100.so")
 
-BF16, F32 = 0, 1
+BF16, F32 = 0, 1  # hrv_dtype codes: 0 = the flavour's 16-bit storage type (bf16 for hrv_<op>, IEEE fp16 for hrv_<op>_f16), 1 = fp32
 ACT_NONE, ACT_RELU, ACT_LRELU, ACT_TANH = 0, 1, 2, 3
 NHWC, NCHW = 0, 1
 EPI_LINEAR, EPI_SPADE = 0, 1
@@ -33,11 +33,30 @@ class ConvParams(ctypes.Structure):
                 ("noise_scale", ctypes.c_void_p), ("gamma_out", Tensor)]
 
 
+FLAVOURED = [n for n in EXPORTS if n not in ("hrv_last_error", "hrv_version", "hrv_device_sm_count")]
+EXPORTS_F16 = [n + "_f16" for n in FLAVOURED]
+
 _lib = None
+_lib_f16 = None
 
 
-def lib():
-    global _lib
+class _F16View:
+    """The fp16-storage flavour of the library: attribute hrv_<op> resolves to the symbol hrv_<op>_f16."""
+
+    def __init__(self, L):
+        self._L = L
+
+    def __getattr__(self, name):
+        return getattr(self._L, name + "_f16" if name in FLAVOURED else name)
+
+
+def lib(dtype=None):
+    """ctypes handle of libhrviton_sm100.so.  dtype torch.float16 selects the fp16-storage flavour of every entry point."""
+    global _lib, _lib_f16
+    if dtype is not None and str(dtype) == "torch.float16":
+        if _lib_f16 is None:
+            _lib_f16 = _F16View(lib())
+        return _lib_f16
     if _lib is not None:
         return _lib
     if not os.path.exists(LIB_PATH):
@@ -71,7 +90,10 @@ def lib():
     L.hrv_l1_bwd.argtypes = [TP, TP, vp, TP, vp]
     L.hrv_pack_conv_weight.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp, vp, i32, i32, vp]
     L.hrv_flow_warp_bwd.argtypes = [vp, vp, vp, TP, TP, vp, vp, vp, vp]
-    for name in EXPORTS:
+    for name in FLAVOURED:
+        twin = getattr(L, name + "_f16")
+        twin.argtypes = getattr(L, name).argtypes
+    for name in EXPORTS + EXPORTS_F16:
         fn = getattr(L, name)
         if name != "hrv_last_error":
             fn.restype = ctypes.c_int

@@ -4,7 +4,7 @@
 
 #include "hrv_host.h"
 
-namespace hrv {
+namespace hrv_host {
 
 static thread_local char g_err[512] = "";
 
@@ -49,8 +49,8 @@ int encode_tensor_map(CUtensorMap* map, int rank, void* base, const cuuint64_t* 
   return HRV_OK;
 }
 
-}  // namespace hrv
+}  // namespace hrv_host
 
-extern "C" const char* hrv_last_error(void) { return hrv::g_err; }
-extern "C" int hrv_version(void) { return 100; }
-extern "C" int hrv_device_sm_count(void) { return hrv::sm_count(); }
+extern "C" const char* hrv_last_error(void) { return hrv_host::g_err; }
+extern "C" int hrv_version(void) { return 200; }
+extern "C" int hrv_device_sm_count(void) { return hrv_host::sm_count(); }

@@ -5,6 +5,16 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#ifdef HRV_F16
+// fp16-storage flavour: the kernel sources are written against the bf16 names; this build maps them onto IEEE half.  Everything
+// between HBM and the fp32 registers (unpack/pack helpers, tcgen05 operand format) follows; TMA moves 2-byte elements either way.
+#include <cuda_fp16.h>
+#define __nv_bfloat16 __half
+#define __nv_bfloat162 __half2
+#define __float2bfloat16 __float2half_rn
+#define __bfloat162float __half2float
+#define __floats2bfloat162_rn __floats2half2_rn
+#endif
 
 namespace hrv {
 
@@ -113,7 +123,12 @@ __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.
 // Instruction descriptor, kind::f16: D=f32 (bits 4-5 = 1), A=B=bf16 (bits 7-9, 10-12 = 1), both K-major
 // (bits 15,16 = 0) unless a_mn/b_mn, N>>3 at bits 17-22, M>>4 at bits 24-28.
 __host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N, uint32_t a_mn = 0, uint32_t b_mn = 0) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (a_mn << 15) | (b_mn << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
+#ifdef HRV_F16
+  return (1u << 4) | (0u << 7) | (0u << 10) |  // A = B = f16 (format code 0)
+#else
+  return (1u << 4) | (1u << 7) | (1u << 10) |
+#endif
+         (a_mn << 15) | (b_mn << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 // Shared-memory matrix descriptor (K-major, swizzled): start>>4 at bits 0-13, LBO>>4 at 16-29 (unused for
 // swizzled K-major when the MMA K extent fits one swizzle row: 1), SBO>>4 at 32-45 (= 8 rows * row bytes),
@@ -124,8 +139,13 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo_
 }
 
 // ---------------------------------------------------------------- misc
+#ifdef HRV_F16
+__device__ __forceinline__ float bf16_lo(uint32_t u) { return __half2float(__ushort_as_half((unsigned short)(u & 0xFFFFu))); }
+__device__ __forceinline__ float bf16_hi(uint32_t u) { return __half2float(__ushort_as_half((unsigned short)(u >> 16))); }
+#else
 __device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
+#endif
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&t);

@@ -9,6 +9,7 @@ from .capi import ACT_LRELU, ACT_NONE, ACT_RELU, ACT_TANH, BF16, F32  # noqa: F4
 
 LAUNCHES = [0]  # count of kernel launches issued through the C-ABI (bench.py reads this for `gpu_launches`)
 PARAM_GEN = [0]  # generation of the parameter values: part of every derived-weight cache key (spade._param_key)
+STORAGE = [torch.bfloat16]  # activation storage type of newly created buffers: torch.bfloat16 (default) or torch.float16
 PROFILE = None  # bench.py sets this to a list; every C-ABI call then appends (kind, work, start_event, end_event)
 
 
@@ -33,6 +34,31 @@ class _Timed:
         return False
 
 
+def set_precision(name):
+    """'bf16' (default: bf16 activations, fp32 accumulation — the training configuration) or 'fp16' (IEEE half activations,
+    3 more mantissa bits: the storage type of the reference's own apex-O1 --fp16 runs, train_generator.py:161-169; meets the
+    1e-2 forward tolerance of BASELINE.json).  Invalidates every derived-weight cache."""
+    dt = {"bf16": torch.bfloat16, "fp16": torch.float16}[name]
+    if STORAGE[0] != dt:
+        STORAGE[0] = dt
+        PARAM_GEN[0] += 1
+
+
+def get_precision():
+    return "fp16" if STORAGE[0] == torch.float16 else "bf16"
+
+
+def _L(*things):
+    """The library flavour matching the storage type of the given Acts / tensors (fp16 if any of them is torch.float16)."""
+    for t in things:
+        if t is None:
+            continue
+        d = t.buf.dtype if isinstance(t, Act) else (t.dtype if torch.is_tensor(t) else t)
+        if d == torch.float16:
+            return capi.lib(torch.float16)
+    return capi.lib()
+
+
 def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -53,7 +79,8 @@ class Act:
         assert self.c0 + self.c <= buf.shape[3]
 
     @staticmethod
-    def empty(n, h, w, c, dtype=torch.bfloat16, device="cuda", pitch=None, zero=False):
+    def empty(n, h, w, c, dtype=None, device="cuda", pitch=None, zero=False):
+        dtype = STORAGE[0] if dtype is None else dtype
         p = round_up(c, 8) if pitch is None else pitch
         f = torch.zeros if zero else torch.empty
         return Act(f((n, h, w, p), dtype=dtype, device=device), c=c)
@@ -69,14 +96,14 @@ class Act:
     def ct(self):
         es = self.buf.element_size()
         return capi.Tensor(self.buf.data_ptr() + self.c0 * es, self.n, self.h, self.w, self.c, self.pitch,
-                           BF16 if self.buf.dtype == torch.bfloat16 else F32)
+                           F32 if self.buf.dtype == torch.float32 else BF16)
 
     def to_nchw(self):
         """fp32 NCHW copy (API boundary / tests)."""
         out = torch.empty((self.n, self.c, self.h, self.w), dtype=torch.float32, device=self.buf.device)
         t = self.ct()
         with _Timed("glue", 0.0, label="nhwc_to_nchw"):
-            capi.check(capi.lib().hrv_nhwc_to_nchw(ctypes.byref(t), out.data_ptr(), _stream()), "nhwc_to_nchw")
+            capi.check(_L(self).hrv_nhwc_to_nchw(ctypes.byref(t), out.data_ptr(), _stream()), "nhwc_to_nchw")
         return out
 
 
@@ -97,7 +124,7 @@ def from_nchw(x, c_pad=None, size=None, out=None):
         out = Act.empty(n, oh, ow, c, pitch=round_up(c if c_pad is None else c_pad, 8))
     t = out.ct()
     with _Timed("glue", 0.0, label="nchw_to_nhwc"):
-        capi.check(capi.lib().hrv_nchw_to_nhwc(x.data_ptr(), c, h, w, ctypes.byref(t), _stream()), "nchw_to_nhwc")
+        capi.check(_L(out).hrv_nchw_to_nhwc(x.data_ptr(), c, h, w, ctypes.byref(t), _stream()), "nchw_to_nhwc")
     return out
 
 
@@ -162,9 +189,9 @@ def pack_weight(w, off, cin_total=None, interleave=None, bn=None, flops_per_pixe
     cin_k = round_up(k_eff, bk)
     bn = pick_bn(rows) if bn is None else bn
     n_pad = round_up(rows, bn)
-    wp = torch.empty((kh * kw, n_pad, cin_k), dtype=torch.bfloat16, device=w.device)
+    wp = torch.empty((kh * kw, n_pad, cin_k), dtype=STORAGE[0], device=w.device)
     with _Timed("glue", 0.0, label="pack_conv_weight"):
-        capi.check(capi.lib().hrv_pack_conv_weight(w.data_ptr(), _p(interleave), cout, cin, kh, kw, 1 if dgrad else 0, None, wp.data_ptr(),
+        capi.check(_L(wp).hrv_pack_conv_weight(w.data_ptr(), _p(interleave), cout, cin, kh, kw, 1 if dgrad else 0, None, wp.data_ptr(),
                                                    n_pad, cin_k, _stream()), "pack_conv_weight")
     fpp = 2.0 * cin * cout * inter * kh * kw if flops_per_pixel is None else flops_per_pixel
     return PackedConv(wp, kh, kw, off[0], off[1], bk, bn, rows, k_eff, fpp)
@@ -218,7 +245,7 @@ def conv2d(inp, pw, out, act=ACT_NONE, scale=None, shift=None, res=None, out_lay
     p.gamma_out = _NULL
     with _Timed("conv", pw.flops_per_pixel * p.out.n * p.out.h * p.out.w,
                 label="%d->%d k%dx%d n%d %dx%d bk%d bn%d" % (inp.c, pw.n_gemm, pw.kh, pw.kw, p.out.n, p.out.h, p.out.w, pw.bk, pw.bn)):
-        capi.check(capi.lib().hrv_conv2d_fwd(ctypes.byref(p), _stream()), "conv2d_fwd")
+        capi.check(_L(inp).hrv_conv2d_fwd(ctypes.byref(p), _stream()), "conv2d_fwd")
     return out
 
 
@@ -242,7 +269,7 @@ def conv2d_spade(actv, pw, out, x0, x0_shift, x1, mean, rstd, noise, noise_scale
     p.gamma_out = gamma_out.ct() if gamma_out is not None else _NULL
     with _Timed("conv_spade", pw.flops_per_pixel * out.n * out.h * out.w,
                 label="%d->%d k%dx%d n%d %dx%d bk%d bn%d" % (actv.c, pw.n_gemm, pw.kh, pw.kw, out.n, out.h, out.w, pw.bk, pw.bn)):
-        capi.check(capi.lib().hrv_conv2d_fwd(ctypes.byref(p), _stream()), "conv2d_fwd(spade)")
+        capi.check(_L(actv).hrv_conv2d_fwd(ctypes.byref(p), _stream()), "conv2d_fwd(spade)")
     return out
 
 
@@ -268,7 +295,7 @@ def instnorm_stats(x0, x0_shift, x1, h, w, noise, noise_scale, eps=1e-5):
     t1 = x1.ct() if x1 is not None else _NULL
     nbytes = n * h * w * (2.0 * c + (4.0 if noise is not None else 0.0))  # one bf16 read of every element (+ noise)
     with _Timed("instnorm_stats", nbytes, launches=3, label="c%d n%d %dx%d shift%d" % (c, n, h, w, x0_shift)):
-        capi.check(capi.lib().hrv_instnorm_stats(ctypes.byref(t0), x0_shift, ctypes.byref(t1), h, w, _p(noise), _p(noise_scale),
+        capi.check(_L(x0).hrv_instnorm_stats(ctypes.byref(t0), x0_shift, ctypes.byref(t1), h, w, _p(noise), _p(noise_scale),
                                                  eps, mean.data_ptr(), rstd.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
                    "instnorm_stats")
     return mean, rstd
@@ -278,7 +305,7 @@ def instnorm_apply(x, mean, rstd, act, out=None):
     out = x if out is None else out
     tx, ty = x.ct(), out.ct()
     with _Timed("glue", 0.0, label="instnorm_apply"):
-        capi.check(capi.lib().hrv_instnorm_apply(ctypes.byref(tx), mean.data_ptr(), rstd.data_ptr(), act, ctypes.byref(ty), _stream()),
+        capi.check(_L(x).hrv_instnorm_apply(ctypes.byref(tx), mean.data_ptr(), rstd.data_ptr(), act, ctypes.byref(ty), _stream()),
                    "instnorm_apply")
     return out
 
@@ -287,7 +314,7 @@ def space_to_depth(x):
     out = Act.empty(x.n, (x.h + 1) // 2, (x.w + 1) // 2, 4 * round_up(x.c, 8))
     tx, ty = x.ct(), out.ct()
     with _Timed("glue", 0.0, label="space_to_depth"):
-        capi.check(capi.lib().hrv_space_to_depth(ctypes.byref(tx), ctypes.byref(ty), _stream()), "space_to_depth")
+        capi.check(_L(x).hrv_space_to_depth(ctypes.byref(tx), ctypes.byref(ty), _stream()), "space_to_depth")
     return out
 
 
@@ -296,7 +323,7 @@ def space_to_depth_bwd(d, n, h, w, c, pitch=None):
     dx = Act.empty(n, h, w, c, pitch=pitch)
     td, tx = d.ct(), dx.ct()
     with _Timed("glue", 0.0, label="space_to_depth_bwd"):
-        capi.check(capi.lib().hrv_space_to_depth_bwd(ctypes.byref(td), ctypes.byref(tx), _stream()), "space_to_depth_bwd")
+        capi.check(_L(d).hrv_space_to_depth_bwd(ctypes.byref(td), ctypes.byref(tx), _stream()), "space_to_depth_bwd")
     return dx
 
 
@@ -304,7 +331,7 @@ def maxpool2(x):
     y = Act.empty(x.n, x.h // 2, x.w // 2, x.c, pitch=x.pitch if x.c0 == 0 else None)
     tx, ty = x.ct(), y.ct()
     with _Timed("glue", 0.0, label="maxpool2_fwd"):
-        capi.check(capi.lib().hrv_maxpool2_fwd(ctypes.byref(tx), ctypes.byref(ty), _stream()), "maxpool2_fwd")
+        capi.check(_L(x).hrv_maxpool2_fwd(ctypes.byref(tx), ctypes.byref(ty), _stream()), "maxpool2_fwd")
     return y
 
 
@@ -312,7 +339,7 @@ def maxpool2_bwd(x, dy):
     dx = Act.empty(x.n, x.h, x.w, x.c, pitch=x.pitch if x.c0 == 0 else None)
     tx, tdy, tdx = x.ct(), dy.ct(), dx.ct()
     with _Timed("glue", 0.0, label="maxpool2_bwd"):
-        capi.check(capi.lib().hrv_maxpool2_bwd(ctypes.byref(tx), ctypes.byref(tdy), ctypes.byref(tdx), _stream()), "maxpool2_bwd")
+        capi.check(_L(x).hrv_maxpool2_bwd(ctypes.byref(tx), ctypes.byref(tdy), ctypes.byref(tdx), _stream()), "maxpool2_bwd")
     return dx
 
 
@@ -320,7 +347,7 @@ def avgpool3s2_bwd(dy, h, w):
     dx = Act.empty(dy.n, h, w, dy.c, pitch=dy.pitch if dy.c0 == 0 else None)
     tdy, tdx = dy.ct(), dx.ct()
     with _Timed("glue", 0.0, label="avgpool3s2_bwd"):
-        capi.check(capi.lib().hrv_avgpool3s2_bwd(ctypes.byref(tdy), ctypes.byref(tdx), _stream()), "avgpool3s2_bwd")
+        capi.check(_L(dy).hrv_avgpool3s2_bwd(ctypes.byref(tdy), ctypes.byref(tdx), _stream()), "avgpool3s2_bwd")
     return dx
 
 
@@ -332,7 +359,7 @@ def im2col(x, kh, kw, pad, k_pad=None):
     out = Act.empty(x.n, x.h, x.w, k_pad)
     tx, to = x.ct(), out.ct()
     with _Timed("glue", 0.0, label="im2col"):
-        capi.check(capi.lib().hrv_im2col(ctypes.byref(tx), ctypes.byref(to), kh, kw, pad, _stream()), "im2col")
+        capi.check(_L(x).hrv_im2col(ctypes.byref(tx), ctypes.byref(to), kh, kw, pad, _stream()), "im2col")
     return out
 
 
@@ -341,7 +368,7 @@ def l1_sum(a, b):
     out = torch.empty(1, dtype=torch.float64, device=a.buf.device)
     ta, tb = a.ct(), b.ct()
     with _Timed("glue", 0.0, label="l1_sum"):
-        capi.check(capi.lib().hrv_l1_sum(ctypes.byref(ta), ctypes.byref(tb), out.data_ptr(), _stream()), "l1_sum")
+        capi.check(_L(a).hrv_l1_sum(ctypes.byref(ta), ctypes.byref(tb), out.data_ptr(), _stream()), "l1_sum")
     return out
 
 
@@ -350,7 +377,7 @@ def l1_bwd(a, b, gscale):
     da = Act.empty(a.n, a.h, a.w, a.c, pitch=a.pitch if a.c0 == 0 else None)
     ta, tb, td = a.ct(), b.ct(), da.ct()
     with _Timed("glue", 0.0, label="l1_bwd"):
-        capi.check(capi.lib().hrv_l1_bwd(ctypes.byref(ta), ctypes.byref(tb), gscale.data_ptr(), ctypes.byref(td), _stream()), "l1_bwd")
+        capi.check(_L(a).hrv_l1_bwd(ctypes.byref(ta), ctypes.byref(tb), gscale.data_ptr(), ctypes.byref(td), _stream()), "l1_bwd")
     return da
 
 
@@ -373,7 +400,7 @@ def avgpool3s2(x):
     out = Act.empty(x.n, (x.h - 1) // 2 + 1, (x.w - 1) // 2 + 1, x.c, pitch=x.pitch if x.c0 == 0 else None)
     tx, ty = x.ct(), out.ct()
     with _Timed("glue", 0.0, label="avgpool3s2"):
-        capi.check(capi.lib().hrv_avgpool3s2(ctypes.byref(tx), ctypes.byref(ty), _stream()), "avgpool3s2")
+        capi.check(_L(x).hrv_avgpool3s2(ctypes.byref(tx), ctypes.byref(ty), _stream()), "avgpool3s2")
     return out
 
 
@@ -381,7 +408,7 @@ def bilinear_up2_add(a, b, out):
     ta, to = a.ct(), out.ct()
     tb = b.ct() if b is not None else _NULL
     with _Timed("glue", 0.0, label="bilinear_up2_add"):
-        capi.check(capi.lib().hrv_bilinear_up2_add(ctypes.byref(ta), ctypes.byref(tb), ctypes.byref(to), _stream()), "bilinear_up2_add")
+        capi.check(_L(a).hrv_bilinear_up2_add(ctypes.byref(ta), ctypes.byref(tb), ctypes.byref(to), _stream()), "bilinear_up2_add")
     return out
 
 
@@ -407,7 +434,7 @@ def flow_warp(flow_lo, src, dst, want_flow_up=True, want_idx=False):
     idx = torch.empty((n, H, W, 2), dtype=torch.int32, device=dev) if want_idx else None
     ts, td = src.ct(), dst.ct()
     with _Timed("glue", 0.0, label="flow_warp"):
-        capi.check(capi.lib().hrv_flow_warp(flow_lo.data_ptr(), linspace_table(W, dev).data_ptr(), linspace_table(H, dev).data_ptr(),
+        capi.check(_L(src, dst).hrv_flow_warp(flow_lo.data_ptr(), linspace_table(W, dev).data_ptr(), linspace_table(H, dev).data_ptr(),
                                             ctypes.byref(ts), ctypes.byref(td), _p(flow_up), _p(idx), _stream()), "flow_warp")
     return flow_up, idx
 
@@ -429,7 +456,7 @@ def norm_bwd(dh, h, gamma, x0, x0_shift, x1, noise, noise_scale, mean, rstd, act
     tx1 = x1.ct() if x1 is not None else _NULL
     tdgb = dgb.ct() if dgb is not None else _NULL
     with _Timed("norm_bwd", n * H * W * C * 2.0 * (4 + (1 if gamma is not None else 0) + (2 if want_dgb else 0)), launches=2):
-        capi.check(capi.lib().hrv_norm_bwd_reduce(ctypes.byref(tdh), ctypes.byref(th), ctypes.byref(tg), ctypes.byref(tx0), x0_shift,
+        capi.check(_L(dh).hrv_norm_bwd_reduce(ctypes.byref(tdh), ctypes.byref(th), ctypes.byref(tg), ctypes.byref(tx0), x0_shift,
                                                   ctypes.byref(tx1), H, W, _p(noise), _p(noise_scale), mean.data_ptr(), rstd.data_ptr(),
                                                   _p(chan_scale), act, ctypes.byref(tdgb), ctypes.byref(tdxn), sums.data_ptr(), _stream()), "norm_bwd_reduce")
     if batch_stats:  # BatchNorm: the two means run over (N,H,W)
@@ -444,7 +471,7 @@ def norm_bwd(dh, h, gamma, x0, x0_shift, x1, noise, noise_scale, mean, rstd, act
     dx0 = Act.empty(n, x0.h, x0.w, c0)
     tdx0 = dx0.ct()
     with _Timed("norm_bwd", n * H * W * c0 * 2.0 * 2, launches=1):
-        capi.check(capi.lib().hrv_norm_bwd_apply(ctypes.byref(tdxn), ctypes.byref(tx0), x0_shift, 0, C, H, W, _p(noise), _p(noise_scale),
+        capi.check(_L(dh).hrv_norm_bwd_apply(ctypes.byref(tdxn), ctypes.byref(tx0), x0_shift, 0, C, H, W, _p(noise), _p(noise_scale),
                                                  mean.data_ptr(), rstd.data_ptr(), m1.data_ptr(), m2.data_ptr(), ctypes.byref(tdx0),
                                                  _p(dns), _stream()), "norm_bwd_apply(x0)")
     dx1 = None
@@ -452,7 +479,7 @@ def norm_bwd(dh, h, gamma, x0, x0_shift, x1, noise, noise_scale, mean, rstd, act
         dx1 = Act.empty(n, H, W, c1)
         tdx1 = dx1.ct()
         with _Timed("norm_bwd", n * H * W * c1 * 2.0 * 3, launches=1):
-            capi.check(capi.lib().hrv_norm_bwd_apply(ctypes.byref(tdxn), ctypes.byref(tx1), 0, c0, C, H, W, _p(noise), _p(noise_scale),
+            capi.check(_L(dh).hrv_norm_bwd_apply(ctypes.byref(tdxn), ctypes.byref(tx1), 0, c0, C, H, W, _p(noise), _p(noise_scale),
                                                      mean.data_ptr(), rstd.data_ptr(), m1.data_ptr(), m2.data_ptr(), ctypes.byref(tdx1),
                                                      _p(dns), _stream()), "norm_bwd_apply(x1)")
     return dgb, dx0, dx1, (dns.float() if dns is not None else None), sums[:, :, 2].sum(0).float(), sums[:, :, 3].sum(0).float()
@@ -469,7 +496,7 @@ def act_bwd_bias(dy, y, act, want_dv=True, want_bias=True):
     ty = y.ct() if (y is not None and act != ACT_NONE) else _NULL
     tdv = dv.ct() if dv is not None else _NULL
     with _Timed("act_bwd", dy.n * dy.h * dy.w * dy.c * 2.0 * (3 if dv is not None else 1)):
-        capi.check(capi.lib().hrv_act_bwd_bias(ctypes.byref(tdy), ctypes.byref(ty), act, ctypes.byref(tdv), _p(bsum), _stream()), "act_bwd_bias")
+        capi.check(_L(dy).hrv_act_bwd_bias(ctypes.byref(tdy), ctypes.byref(ty), act, ctypes.byref(tdv), _p(bsum), _stream()), "act_bwd_bias")
     return (dv if dv is not None else dy), (bsum[:dy.c].float() if bsum is not None else None)
 
 
@@ -479,7 +506,7 @@ def conv2d_wgrad(x, dy, kh, kw, pad):
     tx, tdy = x.ct(), dy.ct()
     with _Timed("wgrad", 2.0 * x.c * dy.c * kh * kw * dy.n * dy.h * dy.w,
                 label="%d->%d k%dx%d n%d %dx%d" % (x.c, dy.c, kh, kw, dy.n, dy.h, dy.w)):
-        capi.check(capi.lib().hrv_conv2d_wgrad(ctypes.byref(tx), ctypes.byref(tdy), kh, kw, pad, dw.data_ptr(), _stream()), "conv2d_wgrad")
+        capi.check(_L(x).hrv_conv2d_wgrad(ctypes.byref(tx), ctypes.byref(tdy), kh, kw, pad, dw.data_ptr(), _stream()), "conv2d_wgrad")
     return dw
 
 
@@ -492,7 +519,7 @@ def batchnorm_stats(x, eps=1e-5):
     rstd_nc = torch.empty_like(mean_nc)
     t0 = x.ct()
     with _Timed("instnorm_stats", n * x.h * x.w * 2.0 * c, launches=3, label="bn c%d n%d %dx%d" % (c, n, x.h, x.w)):
-        capi.check(capi.lib().hrv_instnorm_stats(ctypes.byref(t0), 0, ctypes.byref(_NULL), x.h, x.w, None, None, eps, mean_nc.data_ptr(),
+        capi.check(_L(x).hrv_instnorm_stats(ctypes.byref(t0), 0, ctypes.byref(_NULL), x.h, x.w, None, None, eps, mean_nc.data_ptr(),
                                                  rstd_nc.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "batchnorm_stats")
     sums = ws[: n * c * 16].view(torch.float64).view(n, c, 2).sum(0)  # raw sum / sum of squares left in the workspace
     cnt = float(n * x.h * x.w)
@@ -506,7 +533,7 @@ def norm_apply_affine(x, mean_nc, rstd_nc, gamma, beta, res, act, out=None):
     tx, ty = x.ct(), out.ct()
     tr = res.ct() if res is not None else _NULL
     with _Timed("norm_apply", x.n * x.h * x.w * x.c * 2.0 * (3 if res is not None else 2)):
-        capi.check(capi.lib().hrv_norm_apply_affine(ctypes.byref(tx), mean_nc.data_ptr(), rstd_nc.data_ptr(), _p(gamma), _p(beta),
+        capi.check(_L(x).hrv_norm_apply_affine(ctypes.byref(tx), mean_nc.data_ptr(), rstd_nc.data_ptr(), _p(gamma), _p(beta),
                                                     ctypes.byref(tr), act, ctypes.byref(ty), _stream()), "norm_apply_affine")
     return out
 
@@ -515,7 +542,7 @@ def bilinear_up2_bwd(dout):
     da = Act.empty(dout.n, dout.h // 2, dout.w // 2, dout.c)
     td, ta = dout.ct(), da.ct()
     with _Timed("up2_bwd", dout.n * dout.h * dout.w * dout.c * 2.0 * 1.25):
-        capi.check(capi.lib().hrv_bilinear_up2_bwd(ctypes.byref(td), ctypes.byref(ta), _stream()), "bilinear_up2_bwd")
+        capi.check(_L(dout).hrv_bilinear_up2_bwd(ctypes.byref(td), ctypes.byref(ta), _stream()), "bilinear_up2_bwd")
     return da
 
 
@@ -530,8 +557,8 @@ def flow_warp_bwd(flow_lo, src, ddst, dflow_up_in, want_dsrc=True):
     dflo = torch.empty((n, hl, wl, 2), dtype=torch.float32, device=dev)
     ts, td = src.ct(), ddst.ct()
     with _Timed("flow_warp_bwd", n * H * W * src.c * 2.0 * 3, launches=2):
-        capi.check(capi.lib().hrv_flow_warp_bwd(flow_lo.data_ptr(), linspace_table(W, dev).data_ptr(), linspace_table(H, dev).data_ptr(),
+        capi.check(_L(src, ddst).hrv_flow_warp_bwd(flow_lo.data_ptr(), linspace_table(W, dev).data_ptr(), linspace_table(H, dev).data_ptr(),
                                                 ctypes.byref(ts), ctypes.byref(td), _p(dsrc32), dfu.data_ptr(), dflo.data_ptr(), _stream()),
                    "flow_warp_bwd")
-    dsrc = Act(dsrc32.to(torch.bfloat16)) if want_dsrc else None
+    dsrc = Act(dsrc32.to(src.buf.dtype)) if want_dsrc else None
     return dsrc, dflo

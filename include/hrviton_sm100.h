@@ -10,6 +10,12 @@
  * ("pixel-major") with a channel pitch; kernels are enqueued on the given stream and never allocate
  * or synchronise; every function returns 0 on success or a negative hrv_status, text via
  * hrv_last_error() (thread-local).  There is no CPU fallback.
+ *
+ * Storage flavours: every entry point below exists twice in the library — hrv_<op> keeps activations and packed weights in
+ * bf16 (the training configuration), hrv_<op>_f16 (include/hrviton_sm100_f16.h, generated from this file) keeps them in IEEE
+ * fp16: same signatures, same kernels compiled against the other 16-bit type, tcgen05 operand format f16 instead of bf16.
+ * fp32 buffers (flows, logits, images, statistics, weight gradients) are identical in both.  Wherever a comment says "bf16" read
+ * "the flavour's 16-bit storage type"; hrv_dtype code 0 denotes it.
  */
 #ifndef HRVITON_SM100_H_
 #define HRVITON_SM100_H_
@@ -24,7 +30,7 @@ extern "C" {
 typedef void* hrv_stream; /* cudaStream_t */
 
 enum hrv_status { HRV_OK = 0, HRV_EINVAL = -1, HRV_ECUDA = -2, HRV_EUNSUPPORTED = -3 };
-enum hrv_dtype { HRV_BF16 = 0, HRV_F32 = 1 };
+enum hrv_dtype { HRV_BF16 = 0 /* = the flavour's 16-bit type: bf16 in hrv_<op>, fp16 in hrv_<op>_f16 */, HRV_F32 = 1 };
 enum hrv_act { HRV_ACT_NONE = 0, HRV_ACT_RELU = 1, HRV_ACT_LRELU02 = 2, HRV_ACT_TANH = 3 };
 enum hrv_layout { HRV_NHWC = 0, HRV_NCHW = 1 };
 enum hrv_epilogue { HRV_EPI_LINEAR = 0, HRV_EPI_SPADE = 1 };

@@ -267,10 +267,36 @@ def tocg_forward(sd, input1, input2, bn_train=False):
     return flows, seg, warped_in[:, :-1], warped_in[:, -1:]
 
 
+_SN_TRAIN = [False]
+
+
+class spectral_train:
+    """Train-mode spectral norm for the functional restatements below: one power iteration per forward, u/v updated IN PLACE in
+    the state_dict (no grad), sigma = u.(W v) differentiable through W only — torch.nn.utils.spectral_norm (old style, dim 0,
+    eps 1e-12) as the reference uses it (network_generator.py:138-143)."""
+
+    def __enter__(self):
+        self.old = _SN_TRAIN[0]
+        _SN_TRAIN[0] = True
+        return self
+
+    def __exit__(self, *exc):
+        _SN_TRAIN[0] = self.old
+        return False
+
+
 def spectral_weight(sd, p):
-    """Eval-mode old-style spectral_norm: W_orig / (u . W_mat v)."""
+    """Old-style spectral_norm: W_orig / (u . W_mat v).  Eval mode uses the stored u, v; under `spectral_train()` they are first
+    refreshed by one power iteration (v <- normalize(W^T u), u <- normalize(W v)) written back into sd."""
     w = sd[p + ".weight_orig"]
-    sigma = torch.dot(sd[p + ".weight_u"], torch.mv(w.reshape(w.shape[0], -1), sd[p + ".weight_v"]))
+    wm = w.reshape(w.shape[0], -1)
+    u, v = sd[p + ".weight_u"], sd[p + ".weight_v"]
+    if _SN_TRAIN[0]:
+        with torch.no_grad():
+            v.copy_(F.normalize(torch.mv(wm.detach().t(), u), dim=0, eps=1e-12))
+            u.copy_(F.normalize(torch.mv(wm.detach(), v), dim=0, eps=1e-12))
+        u, v = u.clone(), v.clone()
+    sigma = torch.dot(u, torch.mv(wm, v))
     return w / sigma
 
 

@@ -61,7 +61,7 @@ def main():
     torch.manual_seed(0)
 
     def want(n):
-        return not args.only or args.only == n
+        return (not args.only and n != "big") or args.only == n
 
     with torch.no_grad():
         if want("tocg"):
@@ -99,6 +99,50 @@ def main():
                 finally:
                     torch.randn = real_randn
                 save(tag, seed=seed, shape=[n, h, w], out=out.half(), n_noise=counter[0])  # fp16 storage: 5e-4 abs on (-1,1)
+
+        if want("big"):
+            # ---- the BENCHMARKED shapes (BASELINE.json configs 2-4): 1024x768, generator batch 8, tocg batch 4.  Full outputs
+            # would be 75 MB; the fixture keeps a stride-8 sub-sampling of every output, four full-resolution 64x64 crops and
+            # per-image per-channel sums (fp64) — enough to catch tile-addressing errors anywhere in the >2^31-byte buffers.
+            seed = 23
+            n, h, w = 8, 1024, 768
+            m = ref_gen.SPADEGenerator(gen_opt(h, w), 9).eval()
+            sd = m.state_dict()
+            synth.fill_state_dict(sd, seed)
+            m.load_state_dict(sd)
+            x, seg = synth.gen_inputs(n, h, w, seed)
+            outs = []
+            real_randn = torch.randn
+            for i in range(n):  # eval mode is per-sample independent: one image at a time keeps the CPU footprint small
+                counter = [0]
+
+                def fake_randn(b, ww, hh, one, *a, **k):
+                    t = synth.spade_noise(n, hh, ww, seed, counter[0])[i:i + 1]  # image i's slice of the batch-8 draw
+                    counter[0] += 1
+                    return t[:, None].transpose(1, 3).contiguous()
+
+                torch.randn = fake_randn
+                try:
+                    outs.append(m(x[i:i + 1], seg[i:i + 1]))
+                finally:
+                    torch.randn = real_randn
+                print("gen big image", i, flush=True)
+            out = torch.cat(outs, 0)
+            crops = [(0, 0), (0, w - 64), (h - 64, 0), (h // 2 - 32, w // 2 - 32)]
+            save("gen_1024x768_b8", seed=seed, shape=[n, h, w], sub8=out[:, :, ::8, ::8].half(),
+                 crops=torch.stack([out[:, :, y:y + 64, x0:x0 + 64] for y, x0 in crops], 1).half(), crop_yx=np.asarray(crops),
+                 chan_sums=out.double().sum((2, 3)))
+            seed = 11
+            n = 4
+            m = ref_networks.ConditionGenerator(tocg_opt(), 4, 16, 13, ngf=96, norm_layer=torch.nn.BatchNorm2d).eval()
+            sd = m.state_dict()
+            synth.fill_state_dict(sd, seed)
+            m.load_state_dict(sd)
+            i1, i2 = synth.tocg_inputs(n, h, w, seed)
+            flows, sg, wc, wcm = m(tocg_opt(), i1, i2)
+            save("tocg_1024x768_b4", seed=seed, shape=[n, h, w], seg_sub8=sg[:, :, ::8, ::8], seg_sums=sg.double().sum((2, 3)),
+                 seg_crop=sg[:, :, h - 64:, w - 64:], warped_c_sub8=wc[:, :, ::8, ::8], warped_cm_sub8=wcm[:, :, ::8, ::8],
+                 **{"flow%d_sub" % i: f[:, ::(1 if i < 3 else 4), ::(1 if i < 3 else 4)] for i, f in enumerate(flows)})
 
         if want("gend"):
             seed = 31

@@ -86,4 +86,14 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), "libhrviton_sm100.so does not export %s" % name
     assert set(capi.EXPORTS) == declared
-    assert lib.hrv_version() >= 100
+    # the fp16-storage twins (include/hrviton_sm100_f16.h is generated from the main header: same signatures)
+    hdr16 = open(os.path.join(ROOT, "include", "hrviton_sm100_f16.h")).read()
+    twins = set(re.findall(r"\b(hrv_[a-z0-9_]+_f16)\s*\(", hdr16))
+    assert twins == set(capi.EXPORTS_F16) and len(twins) == len(declared) - 3
+    for name in sorted(twins):
+        assert hasattr(lib, name), "libhrviton_sm100.so does not export %s" % name
+    for name in capi.FLAVOURED:  # twin prototypes are textually the main header's with the suffixed name
+        a = re.search(r"^int %s\(([^;]*?)\);" % name, hdr, flags=re.M | re.S).group(1)
+        b = re.search(r"^int %s_f16\(([^;]*?)\);" % name, hdr16, flags=re.M | re.S).group(1)
+        assert a == b, name
+    assert lib.hrv_version() >= 200

@@ -1,6 +1,7 @@
-"""GPU: gradient parity of the training path (hrviton_b200.autograd_g) against torch autograd run through the CPU
-oracle (fp32) on identical weights / inputs / noise.  bf16 activations: per-parameter relative L2 error < 6e-2 and
-cosine similarity > 0.995."""
+"""GPU: gradient parity of the training path (hrviton_b200.autograd_g / autograd_tocg) against torch autograd run through the
+CPU oracle (fp32) on identical weights / inputs / noise.  Bounds are derived, not hand-picked: the same oracle is re-run with its
+convolutions rounding to bf16 (oracle.storage_rounding, gradients rounded at the same points) and the kernels' per-parameter
+relative L2 errors must stay within 1.1 x that floor in median / p90 (1.25 x in max; 1.6-2 x per individual parameter)."""
 import os
 import sys
 
@@ -15,13 +16,8 @@ from hrviton_b200 import synth  # noqa: E402
 pytestmark = pytest.mark.gpu
 
 
-def test_generator_gradients():
-    import network_generator
-    n, h, w, seed = 1, 512, 384, 23
-    sd = synth_state_dict("gen", seed)
-    x, seg = synth.gen_inputs(n, h, w, seed)
-    R = synth.normalish((n, 3, h, w), seed, "lossw")
-    # ---- oracle: autograd through the functional fp32 restatement (eval-mode spectral norm: no power iteration)
+def _oracle_gen_grads(sd, x, seg, R, seed, rounding=None, sn_train=False):
+    """(out, {name: grad}, state after the forward) of the oracle generator, loss = sum(out * R); optional storage rounding model."""
     sdr = {k: v.clone().requires_grad_(v.is_floating_point() and not k.endswith(("weight_u", "weight_v"))) for k, v in sd.items()}
     cnt = [0]
 
@@ -30,12 +26,64 @@ def test_generator_gradients():
         cnt[0] += 1
         return t
 
-    out_ref = orc.spade_generator_forward(sdr, x, seg, noise_cpu)
-    (out_ref * R).sum().backward()
+    import contextlib
+    with orc.storage_rounding(rounding), (orc.spectral_train() if sn_train else contextlib.nullcontext()):
+        out = orc.spade_generator_forward(sdr, x, seg, noise_cpu)
+    (out * R).sum().backward()
+    return out.detach(), {k: v.grad for k, v in sdr.items() if v.requires_grad and v.grad is not None}, sdr
+
+
+def _rel_rows(grads_got, grads_ref):
+    rows = {}
+    for name, gr in grads_ref.items():
+        g = grads_got[name].detach().float().cpu()
+        nref = float(gr.norm())
+        rows[name] = (float((g - gr).norm()) / (nref + 1e-12), float((g * gr).sum() / (g.norm() * gr.norm() + 1e-20)), nref, float(g.norm()))
+    return rows
+
+
+def _check_against_floor(tag, rows, floor_rows, gmax, per_param_ratio=1.6):
+    """Kernel gradient errors vs the storage-rounded oracle's own errors (both against fp32 oracle autograd).
+    Aggregate statistics carry the 1.1x bound; individual parameters (each a different realisation of the rounding noise) 1.6x."""
+    import floors
+    live = [n for n, r in floor_rows.items() if r[2] > 1e-5 * gmax]
+    dead = [n for n in floor_rows if n not in live]
+    for n in dead:  # mathematically zero gradients (biases feeding an InstanceNorm): ours must be negligible too
+        assert rows[n][3] < 2e-2 * gmax, "%s should have ~zero gradient, got %.3e (max grad norm %.3e)" % (n, rows[n][3], gmax)
+    mine = sorted(rows[n][0] for n in live)
+    flo = sorted(floor_rows[n][0] for n in live)
+    q = lambda v, f: v[min(len(v) - 1, int(len(v) * f))]
+    print("GRADPARITY %s: %d live / %d zero-gradient parameters | kernels median %.3e p90 %.3e max %.3e | rounded-oracle floor median %.3e p90 %.3e max %.3e"
+          % (tag, len(live), len(dead), q(mine, 0.5), q(mine, 0.9), mine[-1], q(flo, 0.5), q(flo, 0.9), flo[-1]))
+    worst = sorted(((rows[n][0] / max(floor_rows[n][0], 1e-9), n) for n in live), reverse=True)[:5]
+    for ratio, n in worst:
+        print("GRADPARITY %s worst ratio x%.2f  ours %.3e floor %.3e cos %.5f  %s" % (tag, ratio, rows[n][0], floor_rows[n][0], rows[n][1], n))
+    assert q(mine, 0.5) <= floors.RATIO * q(flo, 0.5)
+    assert q(mine, 0.9) <= floors.RATIO * q(flo, 0.9)
+    assert mine[-1] <= floors.RATIO_MAX * flo[-1]
+    for n in live:
+        assert rows[n][0] <= per_param_ratio * floor_rows[n][0] + 5e-3, (n, rows[n][0], floor_rows[n][0])
+    return mine, flo
+
+
+@pytest.mark.parametrize("sn_train", [False, True], ids=["eval_sn", "train_sn"])
+def test_generator_gradients(sn_train):
+    """Generator forward + backward vs fp32 oracle autograd.  train_sn: the module is in train() mode, i.e. spectral norm runs its
+    power iteration (u, v refreshed in place, gradient through sigma = u.(W v)) — buffers and gradients are compared with the
+    oracle's train-mode restatement (network_generator.py:138-143)."""
+    import network_generator
+    n, h, w, seed = (1, 512, 384, 23) if not sn_train else (1, 256, 256, 29)
+    sd = synth_state_dict("gen", seed)
+    x, seg = synth.gen_inputs(n, h, w, seed)
+    R = synth.normalish((n, 3, h, w), seed, "lossw")
+    out_ref, g_ref, sd_after = _oracle_gen_grads(sd, x, seg, R, seed, None, sn_train)
+    out_flo, g_flo, _ = _oracle_gen_grads(sd, x, seg, R, seed, torch.bfloat16, sn_train)
+    floor_rows = _rel_rows(g_flo, g_ref)
     # ---- product path
     m = network_generator.SPADEGenerator(gen_opt(h, w, True), 9)
     m.load_state_dict(sd)
-    m = m.cuda().eval()
+    m = m.cuda()
+    m.train(sn_train)
     cnt2 = [0]
 
     def noise_dev(b, hh, ww):
@@ -48,80 +96,108 @@ def test_generator_gradients():
     assert out.requires_grad
     (out * R.cuda()).sum().backward()
     torch.cuda.synchronize()
-    assert float((out.detach().cpu() - out_ref.detach()).abs().max()) < 8e-2
-    rows = []
-    gmax = max(float(sdr[name].grad.norm()) for name, _ in m.named_parameters())
-    for name, p in m.named_parameters():
-        g_ref = sdr[name].grad
-        assert p.grad is not None, name
-        g = p.grad.detach().float().cpu()
-        nref = float(g_ref.norm())
-        rel = float((g - g_ref).norm()) / (nref + 1e-12)
-        cos = float((g * g_ref).sum() / (g.norm() * g_ref.norm() + 1e-20))
-        rows.append((rel, cos, name, nref, float(g.norm())))
+    import floors
+    floors.check("gen train fwd (sn_train=%s)" % sn_train, out.detach(), out_ref.numpy(), floors.stats(out_flo, out_ref.numpy()))
+    if sn_train:  # power iteration: u, v after the forward equal torch's (fp32 gemv both sides)
+        after = m.state_dict()
+        for k in [k for k in sd if k.endswith(("weight_u", "weight_v"))]:
+            assert not torch.equal(sd[k], sd_after[k].detach()), k  # the oracle moved them ...
+            d = float((after[k].cpu() - sd_after[k].detach()).abs().max())
+            assert d < 1e-4, (k, d)                                   # ... and the module moved them identically
+    grads = {name: p.grad for name, p in m.named_parameters() if p.grad is not None}
+    for name in g_ref:
+        assert name in grads, name
+    rows = _rel_rows(grads, g_ref)
+    gmax = max(r[2] for r in rows.values())
     os.makedirs("gpurun_out", exist_ok=True)
-    with open("gpurun_out/gradparity.txt", "w") as f:
-        for rel, cos, name, nref, ng in rows:
-            f.write("%-44s ref %.3e got %.3e rel %.3e cos %.5f\n" % (name, nref, ng, rel, cos))
-    # parameters feeding straight into an InstanceNorm (conv biases, beta biases of shortcut norms) have a mathematically
-    # zero gradient: the oracle shows ~1e-9 round-off there; require ours to be negligible against the largest gradient
-    live = [r for r in rows if r[3] > 1e-5 * gmax]
-    dead = [r for r in rows if r[3] <= 1e-5 * gmax]
-    for r in dead:
-        assert r[4] < 2e-2 * gmax, "%s should have ~zero gradient, got %.3e (max grad norm %.3e)" % (r[2], r[4], gmax)
-    live.sort(reverse=True)
-    for rel, cos, name, nref, ng in live[:10]:
-        print("GRADPARITY worst  rel %.3e cos %.5f  %s" % (rel, cos, name))
-    rels = sorted(r[0] for r in live)
-    print("GRADPARITY generator: %d live / %d zero-gradient parameters, median rel %.3e, p90 %.3e, max %.3e"
-          % (len(live), len(dead), rels[len(rels) // 2], rels[int(len(rels) * 0.9)], rels[-1]))
-    # Reference point (CPU experiment, DESIGN.md "Parity"): the fp32 oracle with its conv inputs/outputs rounded to bf16
-    # deviates from itself by median 0.152 / p90 0.186 / max 0.200 on these gradients (LeakyReLU sign flips of
-    # near-zero pre-activations); the last layer, which sees no such accumulation, must be tight.
-    assert rels[len(rels) // 2] < 0.20 and rels[-1] < 0.30
-    assert min(r[1] for r in live) > 0.97
-    last = {r[2]: r[0] for r in live}
-    assert last["conv_img.weight"] < 3e-2 and last["conv_img.bias"] < 1e-2
+    with open("gpurun_out/gradparity_%s.txt" % ("train_sn" if sn_train else "eval_sn"), "w") as f:
+        for name, (rel, cos, nref, ng) in rows.items():
+            f.write("%-44s ref %.3e got %.3e rel %.3e floor %.3e cos %.5f\n" % (name, nref, ng, rel, floor_rows[name][0], cos))
+    _check_against_floor("generator sn_train=%s" % sn_train, rows, floor_rows, gmax)
+    assert min(r[1] for n_, r in rows.items() if r[2] > 1e-5 * gmax) > 0.97
+    # the last layer sees no accumulated rounding: it must be tight in absolute terms, not only relative to the floor
+    assert rows["conv_img.weight"][0] < 3e-2 and rows["conv_img.bias"][0] < 1e-2
+    assert rows["up_4.norm_0.noise_scale"][2] > 0  # the noise-scale parameters are on the checked path
+
+
+def _d_loss(res):
+    return sum((f * (1 + 0.1 * j)).mean() for fs in res for j, f in enumerate(fs))
+
+
+def _oracle_d_grads(fwd, sd, inp, rounding=None):
+    sdr = {k: v.clone().requires_grad_(v.is_floating_point() and not k.endswith(("weight_u", "weight_v"))) for k, v in sd.items()}
+    inp_ref = inp.clone().requires_grad_(True)
+    with orc.storage_rounding(rounding):
+        res = fwd(sdr, inp_ref)
+    _d_loss(res).backward()
+    grads = {k: v.grad for k, v in sdr.items() if v.requires_grad and v.grad is not None and float(v.grad.norm()) > 1e-7}
+    grads["__input__"] = inp_ref.grad
+    return [[f.detach() for f in fs] for fs in res], grads
+
+
+def _check_d(tag, res, res_ref, res_flo, grads, g_ref, g_flo):
+    import floors
+    for i, fs in enumerate(res):
+        for j, f in enumerate(fs):
+            floors.check("%s d%d_f%d" % (tag, i, j), f.detach(), res_ref[i][j].numpy(), floors.stats(res_flo[i][j], res_ref[i][j].numpy()),
+                         extra_abs=1e-4)
+    rows, floor_rows = _rel_rows(grads, g_ref), _rel_rows(g_flo, g_ref)
+    print("GRADPARITY %s input gradient rel %.3e (floor %.3e)" % (tag, rows["__input__"][0], floor_rows["__input__"][0]))
+    gmax = max(r[2] for r in rows.values())
+    _check_against_floor(tag, rows, floor_rows, gmax, per_param_ratio=2.0)  # tiny maps (9x7 .. 33x25): few samples per parameter
 
 
 def test_discriminator_gradients():
-    """gen-D training path: gradient w.r.t. the input image and all parameters vs torch autograd through the oracle."""
+    """gen-D training path: gradient w.r.t. the input image and all parameters vs torch autograd through the oracle; bounds =
+    1.1 x the bf16-rounded oracle's own deviation."""
     import network_generator
     from hrviton_b200 import autograd_g
     n, h, w, seed = 2, 128, 96, 31
     sd = synth_state_dict("gend", seed)
     x, seg = synth.gen_inputs(n, h, w, seed, input_nc=3)
     inp = torch.cat([seg, x], 1)
-    sdr = {k: v.clone().requires_grad_(v.is_floating_point() and not k.endswith(("weight_u", "weight_v"))) for k, v in sd.items()}
-    inp_ref = inp.clone().requires_grad_(True)
-    res_ref = orc.gen_d_forward(sdr, inp_ref)
-    loss_ref = sum((f * (1 + 0.1 * j)).mean() for fs in res_ref for j, f in enumerate(fs))
-    loss_ref.backward()
+    res_ref, g_ref = _oracle_d_grads(orc.gen_d_forward, sd, inp)
+    res_flo, g_flo = _oracle_d_grads(orc.gen_d_forward, sd, inp, torch.bfloat16)
     m = network_generator.MultiscaleDiscriminator(gen_opt(h, w, True))
     m.load_state_dict(sd)
     m = m.cuda().eval()
     inp_d = inp.cuda().requires_grad_(True)
     res = autograd_g.discriminator_forward_train(m, inp_d, need_wgrad=True)
-    loss = sum((f * (1 + 0.1 * j)).mean() for fs in res for j, f in enumerate(fs))
-    loss.backward()
+    _d_loss(res).backward()
     torch.cuda.synchronize()
-    for i, fs in enumerate(res):
-        for j, f in enumerate(fs):
-            assert float((f.detach().cpu() - res_ref[i][j].detach()).abs().max()) < 3e-2 * max(1.0, float(res_ref[i][j].abs().max()))
-    g, gr = inp_d.grad.cpu(), inp_ref.grad
-    rel_in = float((g - gr).norm() / gr.norm())
-    print("GRADPARITY gen-D input gradient rel %.3e" % rel_in)
-    # InstanceNorm over 9x7 .. 33x25 maps + LeakyReLU sign flips under bf16: same noise regime as the generator test
-    assert rel_in < 0.2
-    rels = []
-    for name, p in m.named_parameters():
-        gr = sdr[name].grad
-        if gr is None or float(gr.norm()) < 1e-7:
-            continue
-        rels.append((float((p.grad.float().cpu() - gr).norm() / gr.norm()), name))
-    rels.sort()
-    print("GRADPARITY gen-D params: median rel %.3e max %.3e (%s)" % (rels[len(rels) // 2][0], rels[-1][0], rels[-1][1]))
-    assert rels[-1][0] < 0.2
+    grads = {name: p.grad for name, p in m.named_parameters() if p.grad is not None}
+    grads["__input__"] = inp_d.grad
+    _check_d("gen-D", res, res_ref, res_flo, grads, g_ref, g_flo)
+
+
+def test_tocg_discriminator_gradients():
+    """Stage-1 discriminator (networks.define_D, LSGAN PatchGAN with InstanceNorm, Ddownx2) through the MODULE's own forward in
+    train mode with grad enabled — the call train_condition.py:208-232 makes — vs oracle autograd (dropout off: it is torch's
+    RNG in the reference too and cannot be replayed)."""
+    import contextlib
+    import io
+
+    import networks
+    seed = 37
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = networks.define_D(input_nc=33, Ddownx2=True, Ddropout=False, n_layers_D=3, spectral=False, num_D=2)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    synth.fill_state_dict(sd, seed)
+    m.load_state_dict(sd)
+    m = m.cuda().train()
+    i1, i2 = synth.tocg_inputs(1, 256, 192, seed)
+    segs = synth.one_hot(synth.labels((1, 256, 192), 13, seed, "dseg"), 13)
+    inp = torch.cat([i1, i2, segs], 1)
+    res_ref, g_ref = _oracle_d_grads(orc.tocg_d_forward, sd, inp)
+    res_flo, g_flo = _oracle_d_grads(orc.tocg_d_forward, sd, inp, torch.bfloat16)
+    inp_d = inp.cuda().requires_grad_(True)
+    res = m(inp_d)  # dispatches to the autograd path
+    assert res[0][0].requires_grad
+    _d_loss(res).backward()
+    torch.cuda.synchronize()
+    grads = {name: p.grad for name, p in m.named_parameters() if p.grad is not None}
+    grads["__input__"] = inp_d.grad
+    _check_d("tocg-D", res, res_ref, res_flo, grads, g_ref, g_flo)
 
 
 def test_stage2_train_step_runs():
@@ -162,50 +238,50 @@ def test_stage2_train_step_runs():
     assert float((D.discriminator_0.model0[0].weight.detach() - d_before).abs().max()) > 0
 
 
+def _oracle_tocg_train(sd, i1, i2, Rs, Rc, rounding=None):
+    sdr = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone()) for k, v in sd.items()}
+    with orc.storage_rounding(rounding):
+        flows_r, seg_r, wc_r, wcm_r = orc.tocg_forward(sdr, i1, i2, bn_train=True)
+    (seg_r * Rs).mean().add((wc_r * Rc).mean()).add(sum(f.abs().mean() for f in flows_r)).backward()
+    grads = {k: v.grad for k, v in sdr.items() if torch.is_tensor(v) and v.requires_grad and v.grad is not None and float(v.grad.norm()) > 1e-7}
+    return [f.detach() for f in flows_r], seg_r.detach(), wc_r.detach(), grads
+
+
 def test_tocg_training_gradients():
-    """Condition generator in train mode (batch-statistics BatchNorm through the statistics kernel + fused backward): outputs and
-    parameter gradients vs torch autograd through the oracle with bn_train=True."""
+    """Condition generator in train mode through the MODULE's forward (the call train_condition.py:158 makes): batch-statistics
+    BatchNorm (statistics kernel + fused backward), outputs and parameter gradients vs torch autograd through the oracle with
+    bn_train=True; bounds = 1.1 x the bf16-rounded oracle's own deviation (train-mode BatchNorm over as few as 4x3x2 samples is
+    ~10x more sensitive to storage rounding than eval mode — for the fp32 algorithm itself)."""
+    import floors
     import networks
     from helpers import tocg_opt
-    from hrviton_b200 import autograd_tocg
     n, h, w, seed = 2, 256, 192, 11
     sd = synth_state_dict("tocg", seed)
     i1, i2 = synth.tocg_inputs(n, h, w, seed)
-    sdr = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone()) for k, v in sd.items()}
-    flows_r, seg_r, wc_r, wcm_r = orc.tocg_forward(sdr, i1, i2, bn_train=True)
-    Rs = synth.normalish(tuple(seg_r.shape), seed, "rs")
-    Rc = synth.normalish(tuple(wc_r.shape), seed, "rc")
-    (seg_r * Rs).mean().add((wc_r * Rc).mean()).add(sum(f.abs().mean() for f in flows_r)).backward()
+    Rs = synth.normalish((n, 13, h, w), seed, "rs")
+    Rc = synth.normalish((n, 3, h, w), seed, "rc")
+    flows_r, seg_r, wc_r, g_ref = _oracle_tocg_train(sd, i1, i2, Rs, Rc)
+    flows_f, seg_f, wc_f, g_flo = _oracle_tocg_train(sd, i1, i2, Rs, Rc, torch.bfloat16)
     m = networks.ConditionGenerator(tocg_opt(True), 4, 16, 13, ngf=96, norm_layer=torch.nn.BatchNorm2d)
     m.load_state_dict(sd)
     m = m.cuda().train()
-    flows, seg, wc, wcm = autograd_tocg.tocg_forward_train(m, i1.cuda(), i2.cuda())
+    flows, seg, wc, wcm = m(i1.cuda(), i2.cuda())  # train mode: forward() dispatches to the differentiable path
+    assert seg.requires_grad
     ((seg * Rs.cuda()).mean() + (wc * Rc.cuda()).mean() + sum(f.abs().mean() for f in flows)).backward()
     torch.cuda.synchronize()
-    rl2 = lambda a, b: float((a.detach().float().cpu() - b.detach()).norm() / b.detach().norm())
-    dseg, dfl = rl2(seg, seg_r), rl2(flows[-1], flows_r[-1])
-    print("TOCGTRAIN forward: relative L2 error seg %.3e, flow4 %.3e" % (dseg, dfl))
-    # batch-statistics BatchNorm over as few as 4x3x2 samples re-amplifies bf16 rounding at every layer (stage-by-stage growth
-    # 0.6% -> 3% measured with tools/check_tocg_train.py; every single op matches torch to 2e-3, tools/check_autograd_ops.py)
-    assert dseg < 8e-2 and dfl < 8e-2
+    floors.check("tocg train seg", seg.detach(), seg_r.numpy(), floors.stats(seg_f, seg_r.numpy()))
+    floors.check("tocg train flow4", flows[-1].detach(), flows_r[-1].numpy(), floors.stats(flows_f[-1], flows_r[-1].numpy()))
+    floors.check("tocg train warped_c", wc.detach(), wc_r.numpy(), floors.stats(wc_f, wc_r.numpy()))
     # running statistics must have moved exactly as torch's BatchNorm2d would move them (momentum 0.1)
     bn = m.ClothEncoder[0].block[1]
     assert int(bn.num_batches_tracked) == 1
-    rows = []
-    for name, p in m.named_parameters():
-        gr = sdr[name].grad
-        if gr is None or p.grad is None or float(gr.norm()) < 1e-7:
-            continue
-        g = p.grad.float().cpu()
-        rows.append((float((g - gr).norm() / gr.norm()), float((g * gr).sum() / (g.norm() * gr.norm() + 1e-20)), name))
-    rows.sort(reverse=True)
-    for r in rows[:5]:
-        print("TOCGTRAIN worst rel %.3e cos %.5f %s" % r)
-    rels = sorted(r[0] for r in rows)
-    print("TOCGTRAIN gradients: %d params, median rel %.3e, max %.3e" % (len(rows), rels[len(rels) // 2], rels[-1]))
-    # Reference point (CPU experiment, same seeds): the fp32 oracle with bf16-rounded conv inputs/outputs deviates from itself by
-    # seg 5.96e-2 / flow 4.86e-2 (forward) and median 0.225 / max 0.466 (gradients) in train mode — 10x its eval-mode sensitivity.
-    assert rels[len(rels) // 2] < 0.30 and rels[-1] < 0.6 and min(r[1] for r in rows) > 0.85
+    grads = {name: p.grad for name, p in m.named_parameters() if p.grad is not None}
+    rows, floor_rows = _rel_rows({k: grads[k] for k in g_ref}, g_ref), _rel_rows({k: g_flo[k] for k in g_ref if k in g_flo}, {k: g_ref[k] for k in g_ref if k in g_flo})
+    rows = {k: rows[k] for k in floor_rows}
+    gmax = max(r[2] for r in rows.values())
+    _check_against_floor("tocg train", rows, floor_rows, gmax, per_param_ratio=2.0)
+    assert min(r[1] for r in rows.values() if r[2] > 1e-5 * gmax) > 0.85
+    assert m.conv2[0].weight.grad is None  # dead branch of the reference (networks.py:131)
 
 
 def test_stage1_train_step_runs():
