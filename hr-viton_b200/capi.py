@@ -13,7 +13,7 @@ EPI_LINEAR, EPI_SPADE = 0, 1
 
 EXPORTS = ["hrv_conv2d_fwd", "hrv_instnorm_stats", "hrv_instnorm_apply", "hrv_norm_apply_affine", "hrv_norm_bwd_reduce", "hrv_norm_bwd_apply", "hrv_act_bwd_bias", "hrv_conv2d_wgrad", "hrv_nchw_to_nhwc", "hrv_nhwc_to_nchw",
            "hrv_space_to_depth", "hrv_avgpool3s2", "hrv_bilinear_up2_add", "hrv_flow_warp", "hrv_bilinear_up2_bwd", "hrv_flow_warp_bwd", "hrv_pack_conv_weight", "hrv_space_to_depth_bwd", "hrv_maxpool2_fwd", "hrv_maxpool2_bwd",
-           "hrv_avgpool3s2_bwd", "hrv_parse_blur_argmax", "hrv_im2col", "hrv_l1_sum", "hrv_l1_bwd", "hrv_last_error",
+           "hrv_avgpool3s2_bwd", "hrv_parse_blur_argmax", "hrv_gaussian_blur", "hrv_flow_warp_nchw", "hrv_im2col", "hrv_l1_sum", "hrv_l1_bwd", "hrv_last_error",
            "hrv_version", "hrv_device_sm_count"]
 
 
@@ -85,6 +85,8 @@ def lib(dtype=None):
     L.hrv_maxpool2_bwd.argtypes = [TP, TP, TP, vp]
     L.hrv_avgpool3s2_bwd.argtypes = [TP, TP, vp]
     L.hrv_parse_blur_argmax.argtypes = [vp, i32, i32, i32, i32, i32, i32, ctypes.POINTER(ctypes.c_int32), i32, vp, vp, vp]
+    L.hrv_gaussian_blur.argtypes = [vp, i32, i32, i32, i32, f32, vp, vp]
+    L.hrv_flow_warp_nchw.argtypes = [vp, i32, i32, i32, vp, vp, vp, i32, i32, i32, vp, i32, i32, f32, f32, vp, vp]
     L.hrv_im2col.argtypes = [TP, TP, i32, i32, i32, vp]
     L.hrv_l1_sum.argtypes = [TP, TP, vp, vp]
     L.hrv_l1_bwd.argtypes = [TP, TP, vp, TP, vp]

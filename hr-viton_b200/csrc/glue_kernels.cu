@@ -195,6 +195,93 @@ __global__ void __launch_bounds__(256) parse_blur_argmax_kernel(const __grid_con
   }
 }
 
+// ---------------------------------------------------------------------------------------------- stand-alone Gaussian blur
+// tgm.image.GaussianBlur((k,k),(sigma,sigma)) on fp32 NCHW planes (train_generator.py:181,247; test_generator.py:91,185): separable,
+// zero padding k/2, normalised 1-D taps — the same arithmetic as the fused parse kernel above, without the resize / arg-max.
+// One block = one 32x32 output tile of one plane.  Used by the torchgeometry shim that lets the reference scripts run unchanged.
+constexpr int kBlurMaxR = 15, kBU = kTile + 2 * kBlurMaxR;  // up to 31 taps
+struct BlurArgs {
+  const float* src;
+  float* dst;
+  int planes, H, W, r;
+  float g[2 * kBlurMaxR + 1];
+};
+__global__ void __launch_bounds__(256) gaussian_blur_kernel(const __grid_constant__ BlurArgs a) {
+  __shared__ float U[kBU][kBU + 1];
+  __shared__ float Hb[kBU][kTile + 1];
+  const int plane = blockIdx.z, ty0 = blockIdx.y * kTile, tx0 = blockIdx.x * kTile, tid = threadIdx.x;
+  const int r = a.r, UU = kTile + 2 * r, taps = 2 * r + 1;
+  const float* s = a.src + (long long)plane * a.H * a.W;
+  for (int i = tid; i < UU * UU; i += 256) {
+    const int uy = i / UU, ux = i - uy * UU;
+    const int Y = ty0 + uy - r, X = tx0 + ux - r;
+    U[uy][ux] = (Y >= 0 && Y < a.H && X >= 0 && X < a.W) ? __ldg(s + (long long)Y * a.W + X) : 0.f;
+  }
+  __syncthreads();
+  for (int i = tid; i < UU * kTile; i += 256) {
+    const int uy = i >> 5, x = i & 31;
+    float acc = 0.f;
+    for (int k = 0; k < taps; ++k) acc = fmaf(a.g[k], U[uy][x + k], acc);
+    Hb[uy][x] = acc;
+  }
+  __syncthreads();
+  const int col = tid & 31, rq = tid >> 5;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int y = rq + 8 * j, Y = ty0 + y, X = tx0 + col;
+    float acc = 0.f;
+    for (int k = 0; k < taps; ++k) acc = fmaf(a.g[k], Hb[y + k][col], acc);
+    if (Y < a.H && X < a.W) a.dst[(long long)plane * a.H * a.W + (long long)Y * a.W + X] = acc;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- hi-res flow warp (planar fp32)
+// train_generator.py:232-238 / test_generator.py:170-176: the 128x96 appearance flow is up-sampled to the cloth's resolution
+// (F.interpolate(size=(H,W), bilinear, align_corners=False), any scale), divided by ((wl-1)/2, (hl-1)/2) [correctly rounded fp32
+// division], added to the linspace base grid and used to grid_sample (bilinear, border) the cloth / cloth mask.  One thread = one
+// output pixel, looping over the few channels (3 + 1): planar reads and writes are coalesced along x.
+__global__ void __launch_bounds__(256) flow_warp_nchw_kernel(const float* __restrict__ flow_lo, int hl, int wl, const float* __restrict__ lin_x,
+                                                            const float* __restrict__ lin_y, const float* __restrict__ src, int C, int Hs, int Ws,
+                                                            float* __restrict__ dst, int H, int W, float div_x, float div_y, float sc_y,
+                                                            float sc_x, float* __restrict__ grid_out, long long npix) {
+  const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= npix) return;
+  const int x = (int)(pix % W), y = (int)((pix / W) % H), n = (int)(pix / ((long long)W * H));
+  // F.interpolate source coordinate: max(scale * (d + 0.5) - 0.5, 0), scale = in/out (area_pixel_compute_source_index)
+  const float fy = fmaxf(__fsub_rn(__fmul_rn(sc_y, __fadd_rn((float)y, 0.5f)), 0.5f), 0.f);
+  const float fx = fmaxf(__fsub_rn(__fmul_rn(sc_x, __fadd_rn((float)x, 0.5f)), 0.5f), 0.f);
+  const int y0 = (int)fy, x0 = (int)fx;
+  const int y1 = min(y0 + 1, hl - 1), x1 = min(x0 + 1, wl - 1);
+  const float ly = __fsub_rn(fy, (float)y0), lx = __fsub_rn(fx, (float)x0);
+  const float hy = __fsub_rn(1.f, ly), hx = __fsub_rn(1.f, lx);
+  const float2* fl = reinterpret_cast<const float2*>(flow_lo) + (long long)n * hl * wl;
+  const float2 f00 = __ldg(fl + (long long)y0 * wl + x0), f01 = __ldg(fl + (long long)y0 * wl + x1);
+  const float2 f10 = __ldg(fl + (long long)y1 * wl + x0), f11 = __ldg(fl + (long long)y1 * wl + x1);
+  // torch upsample_bilinear2d: w_y0 * (w_x0 * v00 + w_x1 * v01) + w_y1 * (w_x0 * v10 + w_x1 * v11)
+  const float ux = __fadd_rn(__fmul_rn(hy, __fadd_rn(__fmul_rn(hx, f00.x), __fmul_rn(lx, f01.x))), __fmul_rn(ly, __fadd_rn(__fmul_rn(hx, f10.x), __fmul_rn(lx, f11.x))));
+  const float uy = __fadd_rn(__fmul_rn(hy, __fadd_rn(__fmul_rn(hx, f00.y), __fmul_rn(lx, f01.y))), __fmul_rn(ly, __fadd_rn(__fmul_rn(hx, f10.y), __fmul_rn(lx, f11.y))));
+  const float gx = __fadd_rn(__fdiv_rn(ux, div_x), __ldg(lin_x + x));
+  const float gy = __fadd_rn(__fdiv_rn(uy, div_y), __ldg(lin_y + y));
+  if (grid_out) reinterpret_cast<float2*>(grid_out)[pix] = make_float2(gx, gy);
+  float ix = __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(gx, 1.f), (float)Ws), 1.f), 2.f);
+  float iy = __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(gy, 1.f), (float)Hs), 1.f), 2.f);
+  ix = fminf(fmaxf(ix, 0.f), (float)(Ws - 1));
+  iy = fminf(fmaxf(iy, 0.f), (float)(Hs - 1));
+  const float bx = floorf(ix), by = floorf(iy);
+  const int sx0 = (int)bx, sy0 = (int)by;
+  const float tx = __fsub_rn(ix, bx), ty = __fsub_rn(iy, by);
+  const int sx1 = min(sx0 + 1, Ws - 1), sy1 = min(sy0 + 1, Hs - 1);
+  const float wx1 = (sx0 + 1 <= Ws - 1) ? tx : 0.f, wy1 = (sy0 + 1 <= Hs - 1) ? ty : 0.f;
+  const float wx0 = 1.f - tx, wy0 = 1.f - ty;
+  const float w00 = wy0 * wx0, w01 = wy0 * wx1, w10 = wy1 * wx0, w11 = wy1 * wx1;
+  const long long plane_s = (long long)Hs * Ws, plane_d = (long long)H * W;
+  const float* sp = src + (long long)n * C * plane_s;
+  float* dp = dst + (long long)n * C * plane_d + (long long)y * W + x;
+  for (int c = 0; c < C; ++c, sp += plane_s, dp += plane_d)
+    *dp = __ldg(sp + (long long)sy0 * Ws + sx0) * w00 + __ldg(sp + (long long)sy0 * Ws + sx1) * w01 + __ldg(sp + (long long)sy1 * Ws + sx0) * w10 +
+          __ldg(sp + (long long)sy1 * Ws + sx1) * w11;
+}
+
 // ---------------------------------------------------------------------------------------------- im2col for tiny-Cin convolutions
 // dst[n,y,x, tap*C + ci] = src[n, y+ky-pad, x+kx-pad, ci] (zero outside / beyond taps*C).  A 3x3 convolution over a 7-channel
 // label map (SPADE's mlp_shared, network_generator.py:182-184) becomes ONE K=64 GEMM block per pixel tile instead of nine K=16
@@ -375,6 +462,32 @@ extern "C" int hrv_parse_blur_argmax(const float* seg, int32_t n, int32_t c, int
   dim3 grid((W + kTile - 1) / kTile, (H + kTile - 1) / kTile, n);
   parse_blur_argmax_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
   return launched("parse_blur_argmax");
+}
+
+extern "C" int hrv_gaussian_blur(const float* src, int32_t planes, int32_t h, int32_t w, int32_t ksize, float sigma, float* dst,
+                                 hrv_stream stream) {
+  if (!src || !dst || planes < 1 || h < 1 || w < 1 || ksize < 1 || !(ksize & 1) || ksize > 2 * kBlurMaxR + 1 || !(sigma > 0.f))
+    return set_error(HRV_EINVAL, "gaussian_blur: odd ksize <= %d, sigma > 0", 2 * kBlurMaxR + 1);
+  BlurArgs a;
+  memset(&a, 0, sizeof(a));
+  a.src = src; a.dst = dst; a.planes = planes; a.H = h; a.W = w; a.r = ksize / 2;
+  float g[2 * kBlurMaxR + 1], fsum = 0.f;
+  for (int k = 0; k < ksize; ++k) { g[k] = expf(-(float)((k - a.r) * (k - a.r)) / (2.f * sigma * sigma)); fsum += g[k]; }
+  for (int k = 0; k < ksize; ++k) a.g[k] = g[k] / fsum;
+  dim3 grid((w + kTile - 1) / kTile, (h + kTile - 1) / kTile, planes);
+  gaussian_blur_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+  return launched("gaussian_blur");
+}
+
+extern "C" int hrv_flow_warp_nchw(const float* flow_lo, int32_t n, int32_t hl, int32_t wl, const float* lin_x, const float* lin_y,
+                                  const float* src, int32_t c, int32_t hs, int32_t ws, float* dst, int32_t h, int32_t w, float div_x,
+                                  float div_y, float* grid_out, hrv_stream stream) {
+  if (!flow_lo || !lin_x || !lin_y || !src || !dst || n < 1 || hl < 1 || wl < 1 || c < 1 || hs < 1 || ws < 1 || h < 1 || w < 1)
+    return set_error(HRV_EINVAL, "flow_warp_nchw: bad arguments");
+  const long long npix = (long long)n * h * w;
+  flow_warp_nchw_kernel<<<nblocks(npix, 256), 256, 0, (cudaStream_t)stream>>>(flow_lo, hl, wl, lin_x, lin_y, src, c, hs, ws, dst, h, w, div_x,
+                                                                             div_y, (float)hl / (float)h, (float)wl / (float)w, grid_out, npix);
+  return launched("flow_warp_nchw");
 }
 
 extern "C" int hrv_im2col(const hrv_tensor* src, const hrv_tensor* dst, int32_t kh, int32_t kw, int32_t pad, hrv_stream stream) {

@@ -26,3 +26,5 @@
 #define hrv_im2col hrv_im2col_f16
 #define hrv_l1_sum hrv_l1_sum_f16
 #define hrv_l1_bwd hrv_l1_bwd_f16
+#define hrv_gaussian_blur hrv_gaussian_blur_f16
+#define hrv_flow_warp_nchw hrv_flow_warp_nchw_f16

@@ -396,6 +396,36 @@ def parse_blur_argmax(seg, size, group_of=None, groups=0, want_idx=True):
     return idx, onehot
 
 
+def gaussian_blur(x, ksize=15, sigma=3.0):
+    """tgm.image.GaussianBlur((ksize,ksize),(sigma,sigma)) on an fp32 NCHW cuda tensor (hrv_gaussian_blur)."""
+    assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 4
+    x = x.contiguous()
+    out = torch.empty_like(x)
+    n, c, h, w = x.shape
+    with _Timed("glue", 0.0, label="gaussian_blur"):
+        capi.check(capi.lib().hrv_gaussian_blur(x.data_ptr(), n * c, h, w, ksize, float(sigma), out.data_ptr(), _stream()), "gaussian_blur")
+    return out
+
+
+def flow_warp_nchw(flow_lo, src, size, div_xy, want_grid=False):
+    """The hi-res cloth warp of the glue (train_generator.py:232-238): flow_lo fp32 (N,hl,wl,2) is up-sampled bilinearly to `size`,
+    divided by div_xy, added to the linspace base grid and used to grid_sample (bilinear, border) src fp32 (N,C,Hs,Ws).
+    Returns (warped (N,C,H,W) fp32, grid (N,H,W,2) | None)."""
+    assert flow_lo.is_cuda and src.is_cuda and flow_lo.dtype == torch.float32 and src.dtype == torch.float32
+    flow_lo, src = flow_lo.contiguous(), src.contiguous()
+    n, hl, wl, _ = flow_lo.shape
+    _, c, hs, ws = src.shape
+    H, W = size
+    dev = src.device
+    out = torch.empty((n, c, H, W), dtype=torch.float32, device=dev)
+    grid = torch.empty((n, H, W, 2), dtype=torch.float32, device=dev) if want_grid else None
+    with _Timed("glue", 0.0, label="flow_warp_nchw"):
+        capi.check(capi.lib().hrv_flow_warp_nchw(flow_lo.data_ptr(), n, hl, wl, linspace_table(W, dev).data_ptr(), linspace_table(H, dev).data_ptr(),
+                                                 src.data_ptr(), c, hs, ws, out.data_ptr(), H, W, float(div_xy[0]), float(div_xy[1]), _p(grid),
+                                                 _stream()), "flow_warp_nchw")
+    return out, grid
+
+
 def avgpool3s2(x):
     out = Act.empty(x.n, (x.h - 1) // 2 + 1, (x.w - 1) // 2 + 1, x.c, pitch=x.pitch if x.c0 == 0 else None)
     tx, ty = x.ct(), out.ct()

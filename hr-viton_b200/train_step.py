@@ -41,15 +41,23 @@ def make_generator_inputs(tocg, batch, fine_h, fine_w, occlusion=False, unfused_
         mask[:, 3:4] = warped_cm
         fake_segmap = fake_segmap * mask
         n, _, ih, iw = c_paired.shape
-        key = (n, ih, iw, str(c_paired.device))
-        if key not in _GRID_CACHE:  # the reference rebuilds this on the CPU and copies it every step (networks.py:162-165)
-            _GRID_CACHE[key] = make_grid(n, ih, iw).to(c_paired.device)
-        grid = _GRID_CACHE[key]
-        flow = F.interpolate(flow_list[-1].permute(0, 3, 1, 2), size=(ih, iw), mode="bilinear").permute(0, 2, 3, 1)
-        flow_norm = torch.cat([flow[..., 0:1] / ((96 - 1.0) / 2.0), flow[..., 1:2] / ((128 - 1.0) / 2.0)], 3)
-        warped_grid = grid + flow_norm
-        warped_cloth = F.grid_sample(c_paired, warped_grid, padding_mode="border", align_corners=False)
-        warped_clothmask = F.grid_sample(cm, warped_grid, padding_mode="border", align_corners=False)
+        if unfused_parse or not c_paired.is_cuda:
+            key = (n, ih, iw, str(c_paired.device))
+            if key not in _GRID_CACHE:  # the reference rebuilds this on the CPU and copies it every step (networks.py:162-165)
+                _GRID_CACHE[key] = make_grid(n, ih, iw).to(c_paired.device)
+            grid = _GRID_CACHE[key]
+            flow = F.interpolate(flow_list[-1].permute(0, 3, 1, 2), size=(ih, iw), mode="bilinear").permute(0, 2, 3, 1)
+            flow_norm = torch.cat([flow[..., 0:1] / ((96 - 1.0) / 2.0), flow[..., 1:2] / ((128 - 1.0) / 2.0)], 3)
+            warped_grid = grid + flow_norm
+            warped_cloth = F.grid_sample(c_paired, warped_grid, padding_mode="border", align_corners=False)
+            warped_clothmask = F.grid_sample(cm, warped_grid, padding_mode="border", align_corners=False)
+        else:
+            # flow up-sampling (x8) + normalisation + base grid + grid_sample of cloth and mask (train_generator.py:232-238): one kernel
+            # per source (hrv_flow_warp_nchw), no (N,H,W,2) grid / flow tensors in HBM
+            from . import ops
+            div = ((96 - 1.0) / 2.0, (128 - 1.0) / 2.0)
+            warped_cloth, _ = ops.flow_warp_nchw(flow_list[-1], c_paired.float(), (ih, iw), div)
+            warped_clothmask, _ = ops.flow_warp_nchw(flow_list[-1], cm.float(), (ih, iw), div)
         if occlusion or unfused_parse:
             fake_parse_gauss = gaussian_blur_15_3(F.interpolate(fake_segmap, size=(ih, iw), mode="bilinear"))
             fake_parse = fake_parse_gauss.argmax(dim=1)[:, None]

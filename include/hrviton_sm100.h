@@ -205,6 +205,20 @@ int hrv_avgpool3s2_bwd(const hrv_tensor* dy, const hrv_tensor* dx, hrv_stream st
 int hrv_parse_blur_argmax(const float* seg, int32_t n, int32_t c, int32_t h, int32_t w, int32_t H, int32_t W,
                           const int32_t* group_of, int32_t groups, int64_t* idx, float* onehot, hrv_stream stream);
 
+/* tgm.image.GaussianBlur((ksize,ksize),(sigma,sigma)) on `planes` fp32 planes of h x w (train_generator.py:181,247;
+ * test_generator.py:91,185): separable, zero padding ksize/2, taps exp(-d^2/(2 sigma^2)) normalised to sum 1; odd ksize <= 31. */
+int hrv_gaussian_blur(const float* src, int32_t planes, int32_t h, int32_t w, int32_t ksize, float sigma, float* dst,
+                      hrv_stream stream);
+
+/* The hi-resolution cloth warp of the glue (train_generator.py:232-238, test_generator.py:170-176) in one kernel:
+ *   flow = F.interpolate(flow_lo (n,hl,wl,2), size=(h,w), bilinear, align_corners=False)      (any scale)
+ *   g = flow / (div_x, div_y) + (lin_x[x], lin_y[y])          (correctly rounded fp32 division; lin_* = torch.linspace(-1,1,w|h))
+ *   dst[n,:,y,x] = grid_sample(src (n,c,hs,ws) fp32 NCHW, g, bilinear, border, align_corners=False)
+ * grid_out (optional): (n,h,w,2) fp32 receives g. */
+int hrv_flow_warp_nchw(const float* flow_lo, int32_t n, int32_t hl, int32_t wl, const float* lin_x, const float* lin_y,
+                       const float* src, int32_t c, int32_t hs, int32_t ws, float* dst, int32_t h, int32_t w, float div_x,
+                       float div_y, float* grid_out, hrv_stream stream);
+
 /* im2col for tiny-Cin convolutions: dst[n,y,x, (ky*kw+kx)*src.c + ci] = src[n, y+ky-pad, x+kx-pad, ci], zero outside the image
  * and in channels >= kh*kw*src.c.  Lets SPADE's 3x3 mlp_shared convolution over the 7-channel label map
  * (network_generator.py:182-184) run as a single K=64 GEMM block (hrv_conv2d_fwd with kh=kw=1) and its weight gradient as a 1x1. */

@@ -16,28 +16,49 @@ import hrviton_oracle as orc  # noqa: E402
 from helpers import load_golden, synth_state_dict  # noqa: E402
 from hrviton_b200 import synth  # noqa: E402
 
-RATIO = 1.1          # kernels may deviate by at most this factor times the rounded oracle's own deviation
-RATIO_MAX = 1.25     # for max|delta|: an extreme-value statistic of 1e5..1e6 samples (two realisations of the same
-                     # rounding noise differ by ~+-10% in their maxima); mean and p99.9 carry the 1.1x bound
+RATIO = 1.1          # kernels may deviate by at most this factor times the rounded oracle's own deviation (mean, tail quantile)
+RATIO_MAX = 1.25     # for max|delta|, an extreme-value statistic: two realisations of the same rounding noise differ by ~10% there
 DT = {"bf16": torch.bfloat16, "fp16": torch.float16}
+# The floor is ONE realisation of the rounding noise and the kernels' error is another (different rounding points inside fused
+# epilogues, different accumulation order), so a ratio of two sample statistics carries sampling noise of its own.  The bounds are
+# therefore RATIO x floor x (1 + 2/sqrt(n_eff)): n_eff = n/16 for the mean (errors are spatially correlated over ~16 samples), the
+# number of samples beyond the quantile for the tail statistic and the maximum.  For the large outputs that matter (>= 1e5 samples)
+# the allowance is below 2% (mean) and the bound is the plain 1.1x; it only widens for tiny tensors (a 8x6x2 flow has 96 samples).
+
+
+def _tail_q(n):
+    """Tail quantile with at least 64 samples beyond it (p99.9 from 64k samples up; None below 640 samples: only mean/max)."""
+    if n < 640:
+        return None
+    return 1.0 - max(64.0, n / 1000.0) / n
 
 
 def stats(got, ref):
     got = got.detach().float().cpu().numpy() if torch.is_tensor(got) else np.asarray(got, np.float32)
-    ref = np.asarray(ref, np.float32)
-    d = np.abs(got - ref)
-    return {"max": float(d.max()), "mean": float(d.mean()), "p999": float(np.quantile(d, 0.999)), "absmax": float(np.abs(ref).max())}
+    ref = ref.detach().float().cpu().numpy() if torch.is_tensor(ref) else np.asarray(ref, np.float32)
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    d = np.abs(got - ref).ravel()
+    q = _tail_q(d.size)
+    return {"max": float(d.max()), "mean": float(d.mean()), "tail": float(np.quantile(d, q)) if q is not None else None, "q": q,
+            "n": int(d.size), "absmax": float(np.abs(ref).max())}
 
 
 def check(name, got, ref, floor, log=print, extra_abs=0.0):
-    """Assert stats(got, ref) <= RATIO * floor (per statistic) and print the measured ratios."""
+    """Assert stats(got, ref) <= RATIO * floor * (1 + sampling allowance), statistic by statistic; prints the measured ratios.
+    `floor` must come from a tensor of the same shape (same sample count) as got/ref."""
     s = stats(got, ref)
-    r = {k: s[k] / max(floor[k], 1e-12) for k in ("max", "mean", "p999")}
-    log("PARITY %-22s max %.3e (floor %.3e, x%.2f)  mean %.3e (floor %.3e, x%.2f)  p99.9 %.3e (x%.2f)  ref absmax %.3g"
-        % (name, s["max"], floor["max"], r["max"], s["mean"], floor["mean"], r["mean"], s["p999"], r["p999"], s["absmax"]))
-    assert s["mean"] <= RATIO * floor["mean"] + extra_abs, (name, "mean", s["mean"], floor["mean"])
-    assert s["p999"] <= RATIO * floor["p999"] + extra_abs, (name, "p99.9", s["p999"], floor["p999"])
-    assert s["max"] <= RATIO_MAX * floor["max"] + extra_abs, (name, "max", s["max"], floor["max"])
+    assert s["n"] == floor["n"], (name, s["n"], floor["n"])
+    n = s["n"]
+    tail_n = n * (1.0 - s["q"]) if s["q"] is not None else float(n)
+    a_mean, a_tail = 1.0 + 2.0 / np.sqrt(max(n / 16.0, 1.0)), 1.0 + 2.0 / np.sqrt(tail_n)
+    r = {k: (s[k] / max(floor[k], 1e-12) if s[k] is not None else float("nan")) for k in ("max", "mean", "tail")}
+    log("PARITY %-34s n=%-8d max %.3e (floor %.3e, x%.2f <= %.2f)  mean %.3e (floor %.3e, x%.2f <= %.2f)  tail[q=%s] x%.2f <= %.2f  ref absmax %.3g"
+        % (name, n, s["max"], floor["max"], r["max"], RATIO_MAX * a_tail, s["mean"], floor["mean"], r["mean"], RATIO * a_mean,
+           ("%.4f" % s["q"]) if s["q"] is not None else "-", r["tail"], RATIO * a_tail, s["absmax"]))
+    assert s["mean"] <= RATIO * a_mean * floor["mean"] + extra_abs, (name, "mean", s["mean"], floor["mean"])
+    if s["q"] is not None:
+        assert s["tail"] <= RATIO * a_tail * floor["tail"] + extra_abs, (name, "tail", s["tail"], floor["tail"])
+    assert s["max"] <= RATIO_MAX * a_tail * floor["max"] + extra_abs, (name, "max", s["max"], floor["max"])
     return s
 
 

@@ -37,7 +37,8 @@ def _gen_floor_image0(g, sd, x, seg, seed, n, precision):
 
     with torch.no_grad(), orc.storage_rounding(floors.DT[precision]):
         out = orc.spade_generator_forward(sd, x[0:1], seg[0:1], noise)
-    return floors.stats(out[:, :, ::8, ::8], g["sub8"][0:1].astype(np.float32))
+    crops = torch.stack([out[:, :, y:y + 64, x0:x0 + 64] for y, x0 in g["crop_yx"]], 1)
+    return floors.stats(out[:, :, ::8, ::8], g["sub8"][0:1].astype(np.float32)), floors.stats(crops, g["crops"][0:1].astype(np.float32))
 
 
 def test_generator_1024x768_b8(precision):
@@ -62,16 +63,19 @@ def test_generator_1024x768_b8(precision):
         out = m(x.cuda(), seg.cuda())
     torch.cuda.synchronize()
     assert out.shape == (n, 3, h, w) and bool(torch.isfinite(out).all())
-    fl = _gen_floor_image0(g, sd, x, seg, seed, n, precision)
+    fl, fl_crops = _gen_floor_image0(g, sd, x, seg, seed, n, precision)
     outc = out.cpu()
-    s = floors.check("%s gen 1024x768 b8 sub8" % precision, outc[:, :, ::8, ::8], g["sub8"].astype(np.float32), fl)
     crops = torch.stack([outc[:, :, y:y + 64, x0:x0 + 64] for y, x0 in g["crop_yx"]], 1)
-    s2 = floors.check("%s gen 1024x768 b8 crops" % precision, crops, g["crops"].astype(np.float32), fl)
+    smax = s2max = 0.0
+    for i in range(n):  # per image against the image-0 floor: same sample count on both sides of every ratio
+        s = floors.check("%s gen 1024x768 img%d sub8" % (precision, i), outc[i:i + 1, :, ::8, ::8], g["sub8"][i:i + 1].astype(np.float32), fl)
+        s2 = floors.check("%s gen 1024x768 img%d crops" % (precision, i), crops[i:i + 1], g["crops"][i:i + 1].astype(np.float32), fl_crops)
+        smax, s2max = max(smax, s["max"]), max(s2max, s2["max"])
     dmean = np.abs(outc.double().sum((2, 3)).numpy() - g["chan_sums"]) / float(h * w)
     print("PARITY %s gen 1024x768 per-image channel-mean error max %.3e (floor mean|d| %.3e)" % (precision, dmean.max(), fl["mean"]))
     assert dmean.max() <= fl["mean"]  # the signed mean error of a whole 786k-pixel plane sits far below the mean |error|
     if precision == "fp16":
-        assert s["max"] < 1e-2 and s2["max"] < 1e-2  # north-star tolerance as written, at the benchmarked shape
+        assert smax < 1e-2 and s2max < 1e-2  # north-star tolerance as written, at the benchmarked shape, every image
 
 
 def test_tocg_1024x768_b4(precision):
@@ -86,20 +90,23 @@ def test_tocg_1024x768_b4(precision):
     i1, i2 = synth.tocg_inputs(n, h, w, seed)
     with torch.no_grad():
         flows, seg, wc, wcm = m(i1.cuda(), i2.cuda())
-        fl_flows, fl_seg, fl_wc, fl_wcm = None, None, None, None
     torch.cuda.synchronize()
-    with torch.no_grad(), orc.storage_rounding(floors.DT[precision]):  # floor on image 0 (eval mode: per-sample independent)
-        rf, rs, rwc, rwcm = orc.tocg_forward(sd, i1[0:1], i2[0:1])
+    with torch.no_grad(), orc.storage_rounding(floors.DT[precision]):  # the rounded oracle on the same 4 images
+        rf, rs, rwc, rwcm = orc.tocg_forward(sd, i1, i2)
     step = lambda i: 1 if i < 3 else 4
-    checks = [("seg_sub8", seg.cpu()[:, :, ::8, ::8], floors.stats(rs[:, :, ::8, ::8], g["seg_sub8"][0:1]), 0.0),
-              ("seg_crop", seg.cpu()[:, :, h - 64:, w - 64:], floors.stats(rs[:, :, ::8, ::8], g["seg_sub8"][0:1]), 0.0),
-              ("warped_c_sub8", wc.cpu()[:, :, ::8, ::8], floors.stats(rwc[:, :, ::8, ::8], g["warped_c_sub8"][0:1]), 0.0),
-              ("warped_cm_sub8", wcm.cpu()[:, :, ::8, ::8], floors.stats(rwcm[:, :, ::8, ::8], g["warped_cm_sub8"][0:1]), 5e-3)]
+    segc, wcc, wcmc = seg.cpu(), wc.cpu(), wcm.cpu()
+    items = [("seg_sub8", segc[:, :, ::8, ::8], rs[:, :, ::8, ::8], 0.0), ("seg_crop", segc[:, :, h - 64:, w - 64:], rs[:, :, h - 64:, w - 64:], 0.0),
+             ("warped_c_sub8", wcc[:, :, ::8, ::8], rwc[:, :, ::8, ::8], 0.0), ("warped_cm_sub8", wcmc[:, :, ::8, ::8], rwcm[:, :, ::8, ::8], 5e-3)]
     for i, f in enumerate(flows):
-        checks.append(("flow%d_sub" % i, f.cpu()[:, ::step(i), ::step(i)], floors.stats(rf[i][:, ::step(i), ::step(i)], g["flow%d_sub" % i][0:1]), 0.0))
-    for key, got, fl, extra in checks:
-        s = floors.check("%s tocg 1024x768 b4 %s" % (precision, key), got, g[key], fl, extra_abs=extra)
-        if precision == "fp16" and not key.startswith("flow"):
-            assert s["max"] < 1e-2 * max(1.0, s["absmax"]), (key, s)
-    dmean = np.abs(seg.cpu().double().sum((2, 3)).numpy() - g["seg_sums"]) / float(h * w)
-    assert dmean.max() <= checks[0][2]["mean"]
+        items.append(("flow%d_sub" % i, f.cpu()[:, ::step(i), ::step(i)], rf[i][:, ::step(i), ::step(i)], 0.0))
+    for key, got, flo, extra in items:
+        for i in range(n):  # image by image: local content (e.g. the 64x64 crop) sets the local error level
+            fl = floors.stats(flo[i:i + 1], g[key][i:i + 1])
+            s = floors.check("%s tocg 1024x768 img%d %s" % (precision, i, key), got[i:i + 1], g[key][i:i + 1], fl, extra_abs=extra)
+            if precision == "fp16" and not key.startswith("flow"):
+                assert s["max"] < 1e-2 * max(1.0, s["absmax"]), (key, s)
+    # whole-plane signed mean error per (image, channel) against the same quantity of the rounded oracle (image 0)
+    dmean = np.abs(segc.double().sum((2, 3)).numpy() - g["seg_sums"]) / float(h * w)
+    dmean_floor = np.abs(rs.double().sum((2, 3)).numpy() - g["seg_sums"]) / float(h * w)
+    print("PARITY %s tocg 1024x768 per-plane mean error max %.3e (rounded oracle %.3e)" % (precision, dmean.max(), dmean_floor.max()))
+    assert dmean.max() <= 2.0 * dmean_floor.max() + 1e-5

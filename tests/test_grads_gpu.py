@@ -61,6 +61,9 @@ def _check_against_floor(tag, rows, floor_rows, gmax, per_param_ratio=1.6):
     assert q(mine, 0.5) <= floors.RATIO * q(flo, 0.5)
     assert q(mine, 0.9) <= floors.RATIO * q(flo, 0.9)
     assert mine[-1] <= floors.RATIO_MAX * flo[-1]
+    cos_mine, cos_flo = min(rows[n][1] for n in live), min(floor_rows[n][1] for n in live)
+    print("GRADPARITY %s: worst cosine kernels %.5f, rounded oracle %.5f" % (tag, cos_mine, cos_flo))
+    assert (1.0 - cos_mine) <= floors.RATIO_MAX * (1.0 - cos_flo) + 1e-3
     for n in live:
         assert rows[n][0] <= per_param_ratio * floor_rows[n][0] + 5e-3, (n, rows[n][0], floor_rows[n][0])
     return mine, flo
@@ -114,7 +117,6 @@ def test_generator_gradients(sn_train):
         for name, (rel, cos, nref, ng) in rows.items():
             f.write("%-44s ref %.3e got %.3e rel %.3e floor %.3e cos %.5f\n" % (name, nref, ng, rel, floor_rows[name][0], cos))
     _check_against_floor("generator sn_train=%s" % sn_train, rows, floor_rows, gmax)
-    assert min(r[1] for n_, r in rows.items() if r[2] > 1e-5 * gmax) > 0.97
     # the last layer sees no accumulated rounding: it must be tight in absolute terms, not only relative to the floor
     assert rows["conv_img.weight"][0] < 3e-2 and rows["conv_img.bias"][0] < 1e-2
     assert rows["up_4.norm_0.noise_scale"][2] > 0  # the noise-scale parameters are on the checked path
@@ -280,7 +282,6 @@ def test_tocg_training_gradients():
     rows = {k: rows[k] for k in floor_rows}
     gmax = max(r[2] for r in rows.values())
     _check_against_floor("tocg train", rows, floor_rows, gmax, per_param_ratio=2.0)
-    assert min(r[1] for r in rows.values() if r[2] > 1e-5 * gmax) > 0.85
     assert m.conv2[0].weight.grad is None  # dead branch of the reference (networks.py:131)
 
 

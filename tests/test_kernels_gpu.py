@@ -428,3 +428,39 @@ def test_conv_pixn_matches_classic_kernel(case):
         ref = ref + b.cpu()[None, :, None, None]
     ref = {0: lambda t: t, 1: torch.relu, 2: lambda t: F.leaky_relu(t, 0.2), 3: torch.tanh}[act](ref)
     assert rel_err(outs[1][..., :cout].permute(0, 3, 1, 2), ref) < 1e-2
+
+
+def test_gaussian_blur_matches_depthwise_conv():
+    """hrv_gaussian_blur vs the restated tgm.image.GaussianBlur (separable depth-wise conv, zero padding) on odd extents."""
+    from hrviton_b200 import train_step
+    x = torch.randn(2, 5, 70, 45)
+    got = ops.gaussian_blur(x.cuda(), 15, 3.0).cpu()
+    want = train_step.gaussian_blur_15_3(x)
+    assert float((got - want).abs().max()) < 2e-6
+    k = torch.arange(7, dtype=torch.float32) - 3
+    g = torch.exp(-(k * k) / (2 * 1.5 * 1.5))
+    g = g / g.sum()
+    w2 = torch.nn.functional.conv2d(torch.nn.functional.conv2d(x, g.view(1, 1, 1, 7).expand(5, 1, 1, 7), padding=(0, 3), groups=5),
+                                    g.view(1, 1, 7, 1).expand(5, 1, 7, 1), padding=(3, 0), groups=5)
+    assert float((ops.gaussian_blur(x.cuda(), 7, 1.5).cpu() - w2).abs().max()) < 2e-6
+
+
+@pytest.mark.parametrize("shape", [((2, 32, 24), (256, 192), 3), ((1, 128, 96), (1024, 768), 4), ((1, 16, 12), (50, 37), 1)])
+def test_flow_warp_nchw_matches_torch_chain(shape):
+    """hrv_flow_warp_nchw (flow up-sampling at any scale + normalise + base grid + grid_sample, train_generator.py:232-238) against the
+    separate torch ops of the reference on the CPU: grid to 2e-6, sampled values to 1e-5 (|src| <= 1)."""
+    import torch.nn.functional as F
+    (n, hl, wl), (H, W), c = shape
+    g = torch.Generator().manual_seed(5)
+    flow = (torch.rand((n, hl, wl, 2), generator=g) - 0.5) * 20.0
+    src = torch.rand((n, c, H, W), generator=g) * 2 - 1
+    div = ((wl - 1.0) / 2.0, (hl - 1.0) / 2.0)
+    up = F.interpolate(flow.permute(0, 3, 1, 2), size=(H, W), mode="bilinear").permute(0, 2, 3, 1)
+    gx = torch.linspace(-1.0, 1.0, W).view(1, 1, W, 1).expand(n, H, W, 1)
+    gy = torch.linspace(-1.0, 1.0, H).view(1, H, 1, 1).expand(n, H, W, 1)
+    grid = torch.cat([up[..., 0:1] / div[0], up[..., 1:2] / div[1]], 3) + torch.cat([gx, gy], 3)
+    want = F.grid_sample(src, grid, padding_mode="border", align_corners=False)
+    got, ggrid = ops.flow_warp_nchw(flow.cuda(), src.cuda(), (H, W), div, want_grid=True)
+    assert float((ggrid.cpu() - grid).abs().max()) < 2e-6
+    # a sample coordinate within 2e-6 (normalised) of a pixel boundary may floor differently: compare values, which are continuous
+    assert float((got.cpu() - want).abs().max()) < 2e-3 and float((got.cpu() - want).abs().mean()) < 1e-5
