@@ -125,14 +125,14 @@ class SpadeFn(torch.autograd.Function):
     gamma|beta GEMM through hrv_conv2d_fwd and its weight gradient."""
 
     @staticmethod
-    def forward(ctx, actv_buf, wg, wb, bg, bb, x0_buf, x1_buf, noise, ns, x0_shift, act):
+    def forward(ctx, actv_buf, wg, wb, bg, bb, x0_buf, x1_buf, noise, ns, x0_shift, act, stats=None):
         n, h, w, _ = actv_buf.shape
         c0 = x0_buf.shape[3]
         c1 = x1_buf.shape[3] if x1_buf is not None else 0
         C = c0 + c1
         x0, x1 = Act(x0_buf), (Act(x1_buf) if x1_buf is not None else None)
         nsd = ns.detach().float().contiguous()
-        mean, rstd = ops.instnorm_stats(x0, x0_shift, x1, h, w, noise, nsd)
+        mean, rstd = stats if stats is not None else ops.instnorm_stats2(x0, x0_shift, x1, h, w, [noise], [nsd])[0]
         gb = ops.pack_weight(wg.detach(), (1, 1), interleave=wb.detach())
         gb_bias = torch.stack([bg.detach(), bb.detach()], 1).reshape(-1).float().contiguous()
         out = Act.empty(n, h, w, C)
@@ -160,7 +160,7 @@ class SpadeFn(torch.autograd.Function):
         dwcat = _wgrad(actv_buf, wg.shape[1], dgb.buf, 2 * C, 3, 3, 1)
         return (dactv, dwcat[0::2].contiguous(), dwcat[1::2].contiguous(), sum_dg, sum_db,
                 dx0.buf if ctx.needs_input_grad[5] else None,
-                dx1.buf if (dx1 is not None and ctx.needs_input_grad[6]) else None, None, dns, None, None)
+                dx1.buf if (dx1 is not None and ctx.needs_input_grad[6]) else None, None, dns, None, None, None)
 
 
 class FromNCHW(torch.autograd.Function):
@@ -195,21 +195,26 @@ def _block_train(blk, x0_buf, x0_shift, x1_buf, seg_buf, noise_fn, out_act):
     # convolution is a single K=64 GEMM block per pixel tile and its weight gradient a 1x1 GEMM
     cols = ops.im2col(Act(seg_buf, c=seg_c), 3, 3, 1).buf if 9 * seg_c <= 64 else None
 
-    def spade(norm, x0b, sh, x1b, act):
+    def spade(norm, x0b, sh, x1b, act, noise=None, stats=None):
         cs = norm.conv_shared[0]
         if cols is not None:
             actv = conv(cols, im2col_weight(cs.weight, cols.shape[3]), cs.bias, act=ACT_RELU, pad=0)
         else:
             actv = conv(seg_buf, cs.weight, cs.bias, act=ACT_RELU)
         return SpadeFn.apply(actv, norm.conv_gamma.weight, norm.conv_beta.weight, norm.conv_gamma.bias, norm.conv_beta.bias,
-                             x0b, x1b, noise_fn(n, h, w), norm.noise_scale, sh, act)
+                             x0b, x1b, noise if noise is not None else noise_fn(n, h, w), norm.noise_scale, sh, act, stats)
 
     if blk.learned_shortcut:
-        hs = spade(blk.norm_s, x0_buf, x0_shift, x1_buf, ACT_NONE)
+        # norm_s and norm_0 share their input (own noise each): one statistics pass over the source tensors serves both
+        nz_s, nz_0 = noise_fn(n, h, w), noise_fn(n, h, w)
+        st_s, st_0 = ops.instnorm_stats2(Act(x0_buf), x0_shift, Act(x1_buf) if x1_buf is not None else None, h, w, [nz_s, nz_0],
+                                         [blk.norm_s.noise_scale.detach().float().contiguous(), blk.norm_0.noise_scale.detach().float().contiguous()])
+        hs = spade(blk.norm_s, x0_buf, x0_shift, x1_buf, ACT_NONE, nz_s, st_s)
         x_s = conv(hs, _conv_weight_train(blk.conv_s, blk.training))
+        h0 = spade(blk.norm_0, x0_buf, x0_shift, x1_buf, ACT_LRELU, nz_0, st_0)
     else:
         x_s = x0_buf
-    h0 = spade(blk.norm_0, x0_buf, x0_shift, x1_buf, ACT_LRELU)
+        h0 = spade(blk.norm_0, x0_buf, x0_shift, x1_buf, ACT_LRELU)
     dx = conv(h0, _conv_weight_train(blk.conv_0, blk.training), blk.conv_0.bias)
     h1 = spade(blk.norm_1, dx, 0, None, ACT_LRELU)
     return conv(h1, _conv_weight_train(blk.conv_1, blk.training), blk.conv_1.bias, res_buf=x_s, act=out_act)

@@ -11,9 +11,9 @@ ACT_NONE, ACT_RELU, ACT_LRELU, ACT_TANH = 0, 1, 2, 3
 NHWC, NCHW = 0, 1
 EPI_LINEAR, EPI_SPADE = 0, 1
 
-EXPORTS = ["hrv_conv2d_fwd", "hrv_instnorm_stats", "hrv_instnorm_apply", "hrv_norm_apply_affine", "hrv_norm_bwd_reduce", "hrv_norm_bwd_apply", "hrv_act_bwd_bias", "hrv_conv2d_wgrad", "hrv_nchw_to_nhwc", "hrv_nhwc_to_nchw",
+EXPORTS = ["hrv_conv2d_fwd", "hrv_instnorm_stats", "hrv_instnorm_stats2", "hrv_instnorm_apply", "hrv_norm_apply_affine", "hrv_norm_bwd_reduce", "hrv_norm_bwd_apply", "hrv_act_bwd_bias", "hrv_conv2d_wgrad", "hrv_nchw_to_nhwc", "hrv_nhwc_to_nchw",
            "hrv_space_to_depth", "hrv_avgpool3s2", "hrv_bilinear_up2_add", "hrv_flow_warp", "hrv_bilinear_up2_bwd", "hrv_flow_warp_bwd", "hrv_pack_conv_weight", "hrv_space_to_depth_bwd", "hrv_maxpool2_fwd", "hrv_maxpool2_bwd",
-           "hrv_avgpool3s2_bwd", "hrv_parse_blur_argmax", "hrv_gaussian_blur", "hrv_flow_warp_nchw", "hrv_im2col", "hrv_l1_sum", "hrv_l1_bwd", "hrv_last_error",
+           "hrv_avgpool3s2_bwd", "hrv_parse_blur_argmax", "hrv_gaussian_blur", "hrv_flow_warp_nchw", "hrv_onehot_u8", "hrv_im2col", "hrv_l1_sum", "hrv_l1_bwd", "hrv_last_error",
            "hrv_version", "hrv_device_sm_count"]
 
 
@@ -67,6 +67,7 @@ def lib(dtype=None):
     TP = ctypes.POINTER(Tensor)
     L.hrv_conv2d_fwd.argtypes = [ctypes.POINTER(ConvParams), vp]
     L.hrv_instnorm_stats.argtypes = [TP, i32, TP, i32, i32, vp, vp, f32, vp, vp, vp, ctypes.c_size_t, vp]
+    L.hrv_instnorm_stats2.argtypes = [TP, i32, TP, i32, i32, vp, vp, vp, vp, f32, vp, vp, vp, vp, vp, ctypes.c_size_t, vp]
     L.hrv_instnorm_apply.argtypes = [TP, vp, vp, i32, TP, vp]
     L.hrv_norm_bwd_reduce.argtypes = [TP, TP, TP, TP, i32, TP, i32, i32, vp, vp, vp, vp, vp, i32, TP, TP, vp, vp]
     L.hrv_norm_apply_affine.argtypes = [TP, vp, vp, vp, vp, TP, i32, TP, vp]
@@ -84,9 +85,10 @@ def lib(dtype=None):
     L.hrv_maxpool2_fwd.argtypes = [TP, TP, vp]
     L.hrv_maxpool2_bwd.argtypes = [TP, TP, TP, vp]
     L.hrv_avgpool3s2_bwd.argtypes = [TP, TP, vp]
-    L.hrv_parse_blur_argmax.argtypes = [vp, i32, i32, i32, i32, i32, i32, ctypes.POINTER(ctypes.c_int32), i32, vp, vp, vp]
+    L.hrv_parse_blur_argmax.argtypes = [vp, i32, i32, i32, i32, i32, i32, ctypes.POINTER(ctypes.c_int32), i32, vp, vp, ctypes.c_uint32, vp, vp]
+    L.hrv_onehot_u8.argtypes = [vp, i32, i32, i32, i32, vp, vp]
     L.hrv_gaussian_blur.argtypes = [vp, i32, i32, i32, i32, f32, vp, vp]
-    L.hrv_flow_warp_nchw.argtypes = [vp, i32, i32, i32, vp, vp, vp, i32, i32, i32, vp, i32, i32, f32, f32, vp, vp]
+    L.hrv_flow_warp_nchw.argtypes = [vp, i32, i32, i32, vp, vp, vp, i32, i32, i32, vp, i32, i32, f32, f32, vp, vp, vp, vp, i32, vp]
     L.hrv_im2col.argtypes = [TP, TP, i32, i32, i32, vp]
     L.hrv_l1_sum.argtypes = [TP, TP, vp, vp]
     L.hrv_l1_bwd.argtypes = [TP, TP, vp, TP, vp]

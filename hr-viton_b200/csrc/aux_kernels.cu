@@ -116,6 +116,124 @@ __global__ void __launch_bounds__(256) instnorm_stats_kernel(View x0, int x0_shi
   }
 }
 
+// ------------------------------------------------------------------------------------------------ IN statistics, fused form
+// Statistics of up to TWO SPADE norms that share one input (norm_s and norm_0 of a block both normalise x = cat(up2(x0), x1), each with
+// its own noise draw and noise scale, network_generator.py:101-113,160-170) from ONE pass over the SOURCE tensors:
+//   sum_P (x_c[P] + nz_j[P] ns_jc)   = S1_c + ns_jc * NZ1_j               S1_c = sum x_c,   NZ1_j = sum nz_j
+//   sum_P (x_c[P] + nz_j[P] ns_jc)^2 = S2_c + 2 ns_jc X_jc + ns_jc^2 NZ2_j   S2_c = sum x_c^2, X_jc = sum x_c nz_j, NZ2_j = sum nz_j^2
+// x0 is read at ITS OWN resolution: with x0_shift = 1 every source pixel stands for its 2x2 children, so S1/S2 count it four times and
+// X_jc pairs it with the sum of the children's noise — 4x fewer bytes than walking the virtual up-sampled tensor, and the second
+// norm costs no second pass.  Segment 0 of the grid (blockIdx.z) covers x0, segment 1 covers x1.  acc: [N][C][4] doubles
+// {S1, S2, X_0, X_1}; nzacc: [N][2][2] doubles {NZ1_j, NZ2_j}.
+__global__ void __launch_bounds__(256) instnorm_stats2_kernel(View xs, int shift, int c_off, int C, int W_full, int G, int PL, int chunk,
+                                                             const float* __restrict__ nz0, const float* __restrict__ nz1,
+                                                             double* __restrict__ acc, double* __restrict__ nzacc, int do_noise_sums) {
+  extern __shared__ float shf[];  // [PL][G*8][4]
+  __shared__ float nzred[8][4];
+  const int n = blockIdx.y;
+  const int g = threadIdx.x % G, pl = threadIdx.x / G;
+  const int Cs = G * 8;
+  const long long HWs = (long long)xs.h * xs.w;           // source pixels
+  const long long HWf = HWs << (2 * shift);               // full-resolution pixels
+  float s[8], q[8], x0a[8], x1a[8], nsum[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { s[i] = 0.f; q[i] = 0.f; x0a[i] = 0.f; x1a[i] = 0.f; }
+  if (pl < PL) {
+    const long long p_begin = (long long)blockIdx.x * chunk;
+    long long p_end = p_begin + chunk;
+    if (p_end > HWs) p_end = HWs;
+    const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(xs.ptr) + (long long)n * HWs * xs.pitch + g * 8;
+    const float* n0 = nz0 ? nz0 + (long long)n * HWf : nullptr;
+    const float* n1 = nz1 ? nz1 + (long long)n * HWf : nullptr;
+    for (long long p = p_begin + pl; p < p_end; p += PL) {
+      const uint4 v = ldg16(base + p * xs.pitch);
+      float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;  // noise sum / sum of squares over the pixel's footprint, per norm
+      if (shift) {
+        const int y = (int)(p / xs.w), x = (int)(p - (long long)y * xs.w);
+        const long long f = (long long)(2 * y) * W_full + 2 * x;
+        if (n0) {
+          const float2 t = __ldg(reinterpret_cast<const float2*>(n0 + f)), u = __ldg(reinterpret_cast<const float2*>(n0 + f + W_full));
+          a0 = (t.x + t.y) + (u.x + u.y);
+          b0 = fmaf(t.x, t.x, fmaf(t.y, t.y, fmaf(u.x, u.x, u.y * u.y)));
+        }
+        if (n1) {
+          const float2 t = __ldg(reinterpret_cast<const float2*>(n1 + f)), u = __ldg(reinterpret_cast<const float2*>(n1 + f + W_full));
+          a1 = (t.x + t.y) + (u.x + u.y);
+          b1 = fmaf(t.x, t.x, fmaf(t.y, t.y, fmaf(u.x, u.x, u.y * u.y)));
+        }
+      } else {
+        if (n0) { a0 = __ldg(n0 + p); b0 = a0 * a0; }
+        if (n1) { a1 = __ldg(n1 + p); b1 = a1 * a1; }
+      }
+      float f8[8];
+      unpack8(v, f8);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        s[i] += f8[i];
+        q[i] = fmaf(f8[i], f8[i], q[i]);
+        x0a[i] = fmaf(f8[i], a0, x0a[i]);
+        x1a[i] = fmaf(f8[i], a1, x1a[i]);
+      }
+      if (g == 0) { nsum[0] += a0; nsum[1] += b0; nsum[2] += a1; nsum[3] += b1; }
+    }
+    float* dst = shf + ((long long)pl * Cs + g * 8) * 4;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { dst[4 * i] = s[i]; dst[4 * i + 1] = q[i]; dst[4 * i + 2] = x0a[i]; dst[4 * i + 3] = x1a[i]; }
+  }
+  __syncthreads();
+  const double mult = (double)(1 << (2 * shift));  // every source pixel stands for 4^shift full-resolution pixels
+  for (int c = threadIdx.x; c < Cs; c += blockDim.x) {
+    double t[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int l = 0; l < PL; ++l) {
+      const float* e = shf + ((long long)l * Cs + c) * 4;
+      t[0] += (double)e[0]; t[1] += (double)e[1]; t[2] += (double)e[2]; t[3] += (double)e[3];
+    }
+    double* a = acc + ((long long)n * C + c_off + c) * 4;
+    atomicAdd(a, t[0] * mult);
+    atomicAdd(a + 1, t[1] * mult);
+    atomicAdd(a + 2, t[2]);
+    atomicAdd(a + 3, t[3]);
+  }
+  if (do_noise_sums) {  // NZ1/NZ2 of both norms: only the g == 0 threads hold contributions; warp reduce, then one atomic per block
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float v = nsum[k];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if ((threadIdx.x & 31) == 0) nzred[threadIdx.x >> 5][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+      double t = 0.0;
+      for (int wv = 0; wv < 8; ++wv) t += (double)nzred[wv][threadIdx.x];
+      atomicAdd(nzacc + (long long)n * 4 + threadIdx.x, t);
+    }
+  }
+}
+
+__global__ void instnorm_finalize2_kernel(const double* __restrict__ acc, const double* __restrict__ nzacc, int N, int C, double inv_hw, float eps,
+                                          const float* __restrict__ ns0, const float* __restrict__ ns1, float* __restrict__ mean0,
+                                          float* __restrict__ rstd0, float* __restrict__ mean1, float* __restrict__ rstd1) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * C) return;
+  const int n = i / C, c = i - n * C;
+  const double S1 = acc[4 * (long long)i], S2 = acc[4 * (long long)i + 1];
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    float* mean = j ? mean1 : mean0;
+    float* rstd = j ? rstd1 : rstd0;
+    if (!mean) continue;
+    const float* nsp = j ? ns1 : ns0;
+    const double ns = nsp ? (double)nsp[c] : 0.0;
+    const double X = acc[4 * (long long)i + 2 + j], NZ1 = nzacc[n * 4 + 2 * j], NZ2 = nzacc[n * 4 + 2 * j + 1];
+    const double m = (S1 + ns * NZ1) * inv_hw;
+    double var = (S2 + 2.0 * ns * X + ns * ns * NZ2) * inv_hw - m * m;
+    if (var < 0.0) var = 0.0;
+    mean[i] = (float)m;
+    rstd[i] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+}
+
 __global__ void instnorm_finalize_kernel(const double* __restrict__ acc, int NC, double inv_hw, float eps,
                                          float* __restrict__ mean, float* __restrict__ rstd) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -411,6 +529,51 @@ extern "C" int hrv_instnorm_stats(const hrv_tensor* x0, int32_t x0_shift, const 
   if ((rc = launch_ok("instnorm_stats"))) return rc;
   instnorm_finalize_kernel<<<blocks_for(N * C, 256), 256, 0, st>>>((const double*)workspace, N * C, 1.0 / (double)HW, eps, mean, rstd);
   return launch_ok("instnorm_finalize");
+}
+
+extern "C" int hrv_instnorm_stats2(const hrv_tensor* x0, int32_t x0_shift, const hrv_tensor* x1, int32_t h, int32_t w, const float* noise0,
+                                   const float* noise_scale0, const float* noise1, const float* noise_scale1, float eps, float* mean0,
+                                   float* rstd0, float* mean1, float* rstd1, void* workspace, size_t workspace_bytes, hrv_stream stream) {
+  int rc = check_bf16_vec(x0, "instnorm_stats2 x0");
+  if (rc) return rc;
+  const bool has1 = x1 && x1->ptr;
+  if (has1 && (rc = check_bf16_vec(x1, "instnorm_stats2 x1"))) return rc;
+  const int C = x0->c + (has1 ? x1->c : 0);
+  if ((x0->c % 8) || (C % 8)) return set_error(HRV_EINVAL, "instnorm_stats2: channel counts must be multiples of 8");
+  if (x0->c / 8 > 256 || (has1 && x1->c / 8 > 256)) return set_error(HRV_EUNSUPPORTED, "instnorm_stats2: more than 2048 channels per source");
+  if (x0_shift < 0 || x0_shift > 1) return set_error(HRV_EINVAL, "instnorm_stats2: x0_shift must be 0 or 1");
+  if ((x0->h << x0_shift) != h || (x0->w << x0_shift) != w) return set_error(HRV_EINVAL, "instnorm_stats2: x0 extent mismatch");
+  if (x0_shift && (w & 1)) return set_error(HRV_EINVAL, "instnorm_stats2: up-sampled width must be even");
+  if (has1 && (x1->h != h || x1->w != w || x1->n != x0->n)) return set_error(HRV_EINVAL, "instnorm_stats2: x1 extent mismatch");
+  if (!mean0 || !rstd0 || ((mean1 == nullptr) != (rstd1 == nullptr))) return set_error(HRV_EINVAL, "instnorm_stats2: outputs");
+  if ((noise0 && !noise_scale0) || (noise1 && !noise_scale1)) return set_error(HRV_EINVAL, "instnorm_stats2: noise without noise_scale");
+  const int N = x0->n;
+  const size_t need = ((size_t)N * C * 4 + (size_t)N * 4) * sizeof(double);
+  if (!workspace || workspace_bytes < need) return set_error(HRV_EINVAL, "instnorm_stats2: workspace too small (%zu < %zu)", workspace_bytes, need);
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(workspace, 0, need, st);
+  double* acc = (double*)workspace;
+  double* nzacc = acc + (size_t)N * C * 4;
+  for (int seg = 0; seg < (has1 ? 2 : 1); ++seg) {
+    const hrv_tensor* xs = seg ? x1 : x0;
+    const int shift = seg ? 0 : x0_shift;
+    const int G = xs->c / 8, PL = 256 / G;
+    const long long HWs = (long long)xs->h * xs->w;
+    long long target_blocks = (long long)sm_count() * 8 / (N > 0 ? N : 1);
+    if (target_blocks < 1) target_blocks = 1;
+    long long chunk = (HWs + target_blocks - 1) / target_blocks;
+    const long long min_chunk = (long long)PL * 16;
+    if (chunk < min_chunk) chunk = min_chunk;
+    const unsigned gx = (unsigned)((HWs + chunk - 1) / chunk);
+    // the noise-only sums are taken once, by the segment that walks the full-resolution grid exactly once per pixel: x0's walk covers
+    // every full-resolution pixel through its footprint, so segment 0 always does it
+    instnorm_stats2_kernel<<<dim3(gx, N), 256, (size_t)PL * G * 8 * 4 * sizeof(float), st>>>(mk(xs), shift, seg ? x0->c : 0, C, w, G, PL, (int)chunk,
+                                                                                             noise0, noise1, acc, nzacc, seg == 0);
+    if ((rc = launch_ok("instnorm_stats2"))) return rc;
+  }
+  instnorm_finalize2_kernel<<<blocks_for(N * C, 256), 256, 0, st>>>(acc, nzacc, N, C, 1.0 / ((double)h * w), eps, noise0 ? noise_scale0 : nullptr,
+                                                                   noise1 ? noise_scale1 : nullptr, mean0, rstd0, mean1, rstd1);
+  return launch_ok("instnorm_finalize2");
 }
 
 extern "C" int hrv_norm_apply_affine(const hrv_tensor* x, const float* mean, const float* rstd, const float* gamma, const float* beta,

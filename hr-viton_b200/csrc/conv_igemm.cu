@@ -28,12 +28,23 @@
 namespace hrv {
 
 constexpr int kMaxStages = 32;
-constexpr int kEpiWG = 4;                       // epilogue warpgroups: each handles every kEpiWG-th 16-column chunk
+constexpr int kEpiWG = 4;                       // pixel-N kernel: epilogue warpgroups (each owns 64 of the tile's 256 pixel columns)
 constexpr int kThreads = 128 + 128 * kEpiWG;  // warps 0-3: TMA / MMA / TMEM-alloc / spare; then the epilogue warpgroups
+// Classic kernel: 3 epilogue warpgroups (each handles every 3rd 16-column chunk) = 512 threads, i.e. 128 registers per thread: room to
+// keep the x operand of every chunk of a tile in flight while the MMAs of that tile still run (see the SPADE epilogue).
+constexpr int kEpiC = 3;
+constexpr int kThreadsC = 128 + 128 * kEpiC;
 
 struct alignas(64) ConvArgs {
   CUtensorMap tmA;
   CUtensorMap tmB;
+  CUtensorMap tmOut;  // staged epilogue: bf16 NHWC output {store_c, W, H, N}, box {64|32 channels, TW, TH, TN}
+  CUtensorMap tmGam;  // staged epilogue: gamma_out of the SPADE training forward
+  CUtensorMap tmOutT, tmGamT;  // the same for the LAST slab of an N tile whose width is not a multiple of 64 columns: box = the remaining
+                               // channels only (dense rows, no swizzle) so that the store never reaches into the next N tile's channels
+  int tail_cols;               // BN % 64 (0: every slab is full)
+  int stage_out;      // 1 = epilogue writes through shared memory + TMA stores (bf16 NHWC outputs); 0 = per-thread global stores
+  uint32_t epi_off;   // byte offset (from the 1 KB aligned base) of the kEpiC staging buffers, epi_wg_bytes each
   int Nimg, Hout, Wout;
   int tw_log, th_log;
   int tiles_x, tiles_y, tiles_img, tiles_n;
@@ -59,10 +70,22 @@ struct alignas(64) ConvArgs {
   __nv_bfloat16* gamma_out;
   int gamma_pitch;
   int pairs, tiles_m, store_c;  // pixel-N variant: 256-pixel tiles (pairs of 128-pixel boxes), channels written per pixel
+  uint32_t epi_wg_bytes, epi_buf_bytes;
+  unsigned long long* stats;    // debug (tools/conv_stall_probe.py): per-CTA cycle counters of the warp roles, or nullptr
 };
 
+__device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+// wait on an mbarrier, optionally accounting the stall cycles (stats != nullptr only under the stall probe)
+__device__ __forceinline__ void mbar_wait_acct(uint32_t bar, uint32_t parity, bool acct, unsigned long long& acc) {
+  if (!acct) { mbar_wait(bar, parity); return; }
+  const long long t0 = clock64();  // try_wait itself may block for a hardware-defined time: time the whole wait
+  mbar_wait(bar, parity);
+  acc += (unsigned long long)(clock64() - t0);
+}
+
 template <int BK>
-__global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvArgs a) {
+__global__ void __launch_bounds__(kThreadsC, 1) conv_igemm_kernel(const __grid_constant__ ConvArgs a) {
   constexpr uint32_t ROW_BYTES = BK * 2;               // one K chunk of one pixel / one output channel
   constexpr uint32_t A_BYTES = 128 * ROW_BYTES;        // 128 pixels
   constexpr uint32_t SBO = 8 * ROW_BYTES;              // 8-row core-matrix group stride
@@ -83,7 +106,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
   const uint32_t NACC = (uint32_t)a.nacc;
   const uint32_t b_bytes = (uint32_t)a.BN * ROW_BYTES;
   const uint32_t stage_bytes = a.halo ? (uint32_t)a.a_stage_bytes : A_BYTES + ((b_bytes + 1023u) & ~1023u);
-  const uint32_t stage0 = base + 2048u;
+  const uint32_t stage0 = base + 2048u + (a.stage_out ? (uint32_t)kEpiC * a.epi_wg_bytes : 0u);  // epilogue staging tiles sit before the rings
   const uint32_t bstage0 = stage0 + (uint32_t)a.stages * stage_bytes;  // halo mode: weight ring after the halo ring
 
   const int warp = threadIdx.x >> 5;
@@ -98,6 +121,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&a.tmA);
     tma_prefetch_desc(&a.tmB);
+    if (a.stage_out) {
+      tma_prefetch_desc(&a.tmOut);
+      if (a.gamma_out) tma_prefetch_desc(&a.tmGam);
+      if (a.tail_cols) {
+        tma_prefetch_desc(&a.tmOutT);
+        if (a.gamma_out) tma_prefetch_desc(&a.tmGamT);
+      }
+    }
   } else if (warp == 1 && lane == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(bar_full(s), 1);
@@ -109,7 +140,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
     }
     for (int i = 0; i < a.nacc; ++i) {
       mbar_init(bar_tfull(i), 1);
-      mbar_init(bar_tempty(i), 128 * kEpiWG);
+      mbar_init(bar_tempty(i), 128 * kEpiC);
     }
     fence_mbar_init();
   } else if (warp == 2) {
@@ -120,6 +151,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+  const bool acct = a.stats != nullptr;
+  unsigned long long w0 = 0, w1 = 0, w2 = 0;  // stall cycles per barrier class of this warp's role
+  const long long t_begin = acct ? clock64() : 0;
 
   if (warp == 0) {
     // ===================================================== TMA producer (whole warp, warp-uniform; one elected lane issues)
@@ -152,7 +186,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
               ay0 = (tya << a.th_log) - a.off_y;
               a_decode = false;
             }
-            mbar_wait(bar_empty(as), aph ^ 1u);
+            mbar_wait_acct(bar_empty(as), aph ^ 1u, acct, w0);
             if (elect_one()) {
               mbar_arrive_expect_tx(bar_full(as), (uint32_t)a.a_stage_bytes_tx);
               tma_load_4d(a_addr, &a.tmA, bar_full(as), akc * BK, ax0, ay0, an0);
@@ -164,7 +198,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
             if (++akc == a.chunks) { akc = 0; atile += gridDim.x; a_decode = true; }
           }
           for (int t0 = 0; t0 < taps; t0 += a.tpb) {
-            mbar_wait(bar_bempty(bs), bph ^ 1u);
+            mbar_wait_acct(bar_bempty(bs), bph ^ 1u, acct, w1);
             if (elect_one()) {
               mbar_arrive_expect_tx(bar_bfull(bs), b_tx);
               tma_load_3d(b_addr, &a.tmB, bar_bfull(bs), kc * BK, nt * a.BN, t0);
@@ -193,7 +227,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
         for (int ky = 0; ky < a.KH; ++ky) {
           for (int kx = 0; kx < a.KW; ++kx, ++tap) {
             for (int kc = 0; kc < a.chunks; ++kc) {
-              mbar_wait(bar_empty(st), ph ^ 1u);
+              mbar_wait_acct(bar_empty(st), ph ^ 1u, acct, w0);
               if (elect_one()) {
                 mbar_arrive_expect_tx(bar_full(st), tx_bytes);
                 tma_load_4d(sa, &a.tmA, bar_full(st), kc * BK, x0 + kx, y0 + ky, n0);
@@ -207,6 +241,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
         }
       }
     }
+    if (acct && lane == 0) { a.stats[blockIdx.x * 16 + 4] = w0; a.stats[blockIdx.x * 16 + 5] = w1; }
   } else if (warp == 1) {
     // ===================================================== MMA issuer (whole warp, warp-uniform; one elected lane issues)
     const uint32_t idesc = make_idesc_bf16(128, (uint32_t)a.BN);
@@ -220,16 +255,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0, a_addr = stage0, b_addr = bstage0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        mbar_wait(bar_tempty(acc), acc_ph ^ 1u);
+        mbar_wait_acct(bar_tempty(acc), acc_ph ^ 1u, acct, w2);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * (uint32_t)a.BN;
         uint32_t accumulate = 0;
         for (int kc = 0; kc < a.chunks; ++kc) {
-          mbar_wait(bar_full(as), aph);
+          mbar_wait_acct(bar_full(as), aph, acct, w0);
           uint32_t sa_tap = a_addr;  // shifted view of the halo tile, advanced tap by tap
           int kx = 0;
           for (int t0 = 0; t0 < taps; t0 += a.tpb) {
-            mbar_wait(bar_bfull(bs), bph);
+            mbar_wait_acct(bar_bfull(bs), bph, acct, w1);
             tc_fence_after();
             uint32_t sb_tap = b_addr;
             for (int t = 0; t < a.tpb; ++t) {
@@ -264,11 +299,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
       int st = 0;
       uint32_t ph = 0, sa = stage0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        mbar_wait(bar_tempty(acc), acc_ph ^ 1u);
+        mbar_wait_acct(bar_tempty(acc), acc_ph ^ 1u, acct, w2);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * (uint32_t)a.BN;
         for (int k = 0; k < KT; ++k) {
-          mbar_wait(bar_full(st), ph);
+          mbar_wait_acct(bar_full(st), ph, acct, w0);
           tc_fence_after();
           const uint64_t da = da_hi | (uint64_t)((sa & 0x3FFFFu) >> 4);
           const uint64_t db = db_hi | (uint64_t)(((sa + A_BYTES) & 0x3FFFFu) >> 4);
@@ -286,14 +321,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
         if (++acc == NACC) { acc = 0; acc_ph ^= 1u; }
       }
     }
+    if (acct && lane == 0) {
+      unsigned long long* o = a.stats + blockIdx.x * 16;
+      o[0] = (unsigned long long)(clock64() - t_begin); o[1] = w0; o[2] = w1; o[3] = w2;
+      o[8] = (unsigned long long)((total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1);
+    }
   } else if (warp >= 4) {
     // ===================================================== epilogue (one TMEM lane = one pixel per thread)
     const int q = warp & 3;             // TMEM lane quarter this warp may access
-    const int wg = (warp - 4) >> 2;     // epilogue warpgroup: owns 16-column chunks wg, wg+kEpiWG, ...
+    const int wg = (warp - 4) >> 2;     // epilogue warpgroup: owns 16-column chunks wg, wg+kEpiC, ...
     const int r = q * 32 + lane;
     const int tw_mask = (1 << a.tw_log) - 1, th_mask = (1 << a.th_log) - 1;
-    uint32_t acc = 0, aph = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    uint32_t acc = 0, aph = 0, tile_it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_it) {
       const int nt = tile % a.tiles_n;
       int mt = tile / a.tiles_n;
       const int tx = mt % a.tiles_x;
@@ -307,14 +347,181 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
       const long long pix = ((long long)n * a.Hout + y) * a.Wout + x;
 
       const int n_base = nt * a.BN;
-      mbar_wait(bar_tfull(acc), aph);
-      tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)a.BN;
 
-      if (a.epi == 0) {
+      if (a.stage_out) {
+        // ================= staged epilogue (bf16 NHWC outputs): the tile's output leaves through shared memory and TMA stores.
+        // Per-thread global stores write 16 bytes at the pixel pitch — 32 different lines per warp instruction — and that LSU
+        // traffic, not the tensor pipe, bounded every wide-N convolution (tools/conv_stall_probe.py, profiles/r2_conv_stall*.txt).
+        // Work unit = one SLAB of 64 GEMM columns (LINEAR: 64 channels = 128-byte rows, SWIZZLE_128B; SPADE: 32 channels of
+        // (gamma,beta) pairs = 64-byte rows, SWIZZLE_64B); slab s of tile number t belongs to warpgroup (s + t) mod kEpiC, which
+        // converts it into its private staging tile [128 pixels][row] and has one thread issue the TMA store (the tensor map clips
+        // pixels / channels outside the tensor).
+        const bool spade = a.epi != 0;
+        const uint32_t so = base + a.epi_off + (uint32_t)wg * a.epi_wg_bytes;  // staging tile of the output
+        const uint32_t sg = so + a.epi_buf_bytes;                                // ... and of gamma_out (SPADE training forward)
+        const int n_slabs = (a.BN + 63) >> 6;
+        const int tile_x0 = tx << a.tw_log, tile_y0 = ty << a.th_log, tile_n0 = ti << (7 - a.tw_log - a.th_log);
+        const int sh0 = a.x0_shift;
+        const long long pix0 = spade ? ((long long)n * (a.Hout >> sh0) + (y >> sh0)) * (a.Wout >> sh0) + (x >> sh0) : 0;
+        const float nz = (spade && valid && a.noise) ? __ldg(a.noise + pix) : 0.f;
+        bool waited = false;
+        for (int sl = (wg + kEpiC - (int)(tile_it % kEpiC)) % kEpiC; sl < n_slabs; sl += kEpiC) {
+          const int colb = sl * 64;
+          const bool tail = a.tail_cols != 0 && sl == n_slabs - 1;  // narrower last slab: dense rows of tail_cols (LINEAR) / tail_cols/2 (SPADE) channels
+          const uint32_t trow = (uint32_t)a.tail_cols * (spade ? 1u : 2u);  // its row pitch in bytes
+          // ---- operands that do not depend on the accumulator go first: x (SPADE) / residual (LINEAR) of the slab's 4 chunks
+          uint4 pre[4][2];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            pre[k][0] = make_uint4(0, 0, 0, 0);
+            pre[k][1] = make_uint4(0, 0, 0, 0);
+            const int col = colb + k * 16;
+            if (col >= a.BN || !valid) continue;
+            if (spade) {
+              const int c0 = (n_base + col) >> 1;
+              if (c0 < a.C_mod) {
+                const __nv_bfloat16* xp = (c0 < a.x0_c) ? (a.x0 + pix0 * a.x0_pitch + c0) : (a.x1 + pix * a.x1_pitch + (c0 - a.x0_c));
+                pre[k][0] = __ldg(reinterpret_cast<const uint4*>(xp));
+              }
+            } else if (a.res && a.res_dtype == 0) {
+              const int j0 = n_base + col;
+              const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(a.res) + pix * a.res_pitch + j0;
+              if (j0 < a.out_c) pre[k][0] = __ldg(reinterpret_cast<const uint4*>(rp));
+              if (j0 + 8 < a.out_c) pre[k][1] = __ldg(reinterpret_cast<const uint4*>(rp) + 1);
+            }
+          }
+          if (!waited) {
+            mbar_wait_acct(bar_tfull(acc), aph, acct, w0);
+            tc_fence_after();
+            waited = true;
+          }
+          // ---- the previous TMA store of this warpgroup must have finished reading the staging tile
+          if (r == 0) bulk_wait_read<0>();
+          named_bar_sync(1 + wg, 128);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int col = colb + k * 16;
+            if (col >= a.BN) break;
+            uint32_t v[16];
+            __syncwarp();
+            tmem_ld16(taddr + col, v);
+            tmem_wait_ld();
+            if (spade) {
+              const int c0 = (n_base + col) >> 1;
+              float o[8], gmv[8];
+              if (c0 < a.C_mod) {
+                float mu[8], rs[8], nsv[8], sh[16];
+                const float4* mp = reinterpret_cast<const float4*>(a.mean + (long long)(valid ? n : 0) * a.C_mod + c0);
+                const float4* rp = reinterpret_cast<const float4*>(a.rstd + (long long)(valid ? n : 0) * a.C_mod + c0);
+                *reinterpret_cast<float4*>(mu) = __ldg(mp);
+                *reinterpret_cast<float4*>(mu + 4) = __ldg(mp + 1);
+                *reinterpret_cast<float4*>(rs) = __ldg(rp);
+                *reinterpret_cast<float4*>(rs + 4) = __ldg(rp + 1);
+                if (a.noise_scale) {
+                  const float4* np_ = reinterpret_cast<const float4*>(a.noise_scale + c0);
+                  *reinterpret_cast<float4*>(nsv) = __ldg(np_);
+                  *reinterpret_cast<float4*>(nsv + 4) = __ldg(np_ + 1);
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) nsv[i] = 0.f;
+                }
+                if (a.shift) {
+                  const float4* sp = reinterpret_cast<const float4*>(a.shift + 2 * c0);
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(sh + 4 * i) = __ldg(sp + i);
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) sh[i] = 0.f;
+                }
+                const uint4 xk = pre[k][0];
+                const float xs[8] = {bf16_lo(xk.x), bf16_hi(xk.x), bf16_lo(xk.y), bf16_hi(xk.y),
+                                     bf16_lo(xk.z), bf16_hi(xk.z), bf16_lo(xk.w), bf16_hi(xk.w)};
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float xval = fmaf(nz, nsv[i], xs[i]);
+                  const float gm = __uint_as_float(v[2 * i]) + sh[2 * i];
+                  const float bt = __uint_as_float(v[2 * i + 1]) + sh[2 * i + 1];
+                  const float xn = (xval - mu[i]) * rs[i];
+                  gmv[i] = gm;
+                  o[i] = apply_act(fmaf(xn, 1.f + gm, bt), a.act);
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { o[i] = 0.f; gmv[i] = 0.f; }
+              }
+              // 64-byte rows, SWIZZLE_64B: 16-byte piece k of row r lives at piece k ^ ((r >> 1) & 3); the tail slab is dense
+              const uint32_t off = tail ? (uint32_t)r * trow + (uint32_t)(k << 4) : (uint32_t)r * 64u + (uint32_t)((k ^ ((r >> 1) & 3)) << 4);
+              st_shared_v4(so + off, make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7])));
+              if (a.gamma_out)
+                st_shared_v4(sg + off, make_uint4(pack_bf16(gmv[0], gmv[1]), pack_bf16(gmv[2], gmv[3]), pack_bf16(gmv[4], gmv[5]), pack_bf16(gmv[6], gmv[7])));
+            } else {
+#pragma unroll
+              for (int g = 0; g < 2; ++g) {
+                const int jg = n_base + col + g * 8;
+                float f[8];
+                if (jg + 8 <= a.n_gemm) {  // vector path (scale/shift arrays are 16-byte aligned torch allocations)
+                  float sc[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f}, sh[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                  if (a.scale) {
+                    *reinterpret_cast<float4*>(sc) = __ldg(reinterpret_cast<const float4*>(a.scale + jg));
+                    *reinterpret_cast<float4*>(sc + 4) = __ldg(reinterpret_cast<const float4*>(a.scale + jg) + 1);
+                  }
+                  if (a.shift) {
+                    *reinterpret_cast<float4*>(sh) = __ldg(reinterpret_cast<const float4*>(a.shift + jg));
+                    *reinterpret_cast<float4*>(sh + 4) = __ldg(reinterpret_cast<const float4*>(a.shift + jg) + 1);
+                  }
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) f[i] = fmaf(__uint_as_float(v[g * 8 + i]), sc[i], sh[i]);
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) {
+                    const int j = jg + i;
+                    const bool in = j < a.n_gemm;
+                    const float sc = in ? (a.scale ? __ldg(a.scale + j) : 1.f) : 0.f;
+                    const float sh = (in && a.shift) ? __ldg(a.shift + j) : 0.f;
+                    f[i] = fmaf(__uint_as_float(v[g * 8 + i]), sc, sh);
+                  }
+                }
+                if (a.res) {
+                  if (a.res_dtype == 0) {
+                    const uint4 rv = pre[k][g];
+                    f[0] += bf16_lo(rv.x); f[1] += bf16_hi(rv.x); f[2] += bf16_lo(rv.y); f[3] += bf16_hi(rv.y);
+                    f[4] += bf16_lo(rv.z); f[5] += bf16_hi(rv.z); f[6] += bf16_lo(rv.w); f[7] += bf16_hi(rv.w);
+                  } else if (valid) {
+                    const float* rp = reinterpret_cast<const float*>(a.res) + pix * a.res_pitch + jg;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                      if (jg + i < a.out_c) f[i] += __ldg(rp + i);
+                  }
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[i] = apply_act(f[i], a.act);
+                // 128-byte rows, SWIZZLE_128B: 16-byte piece p of row r lives at piece p ^ (r & 7); the tail slab is dense
+                const int pc = 2 * k + g;
+                st_shared_v4(so + (tail ? (uint32_t)r * trow + (uint32_t)(pc << 4) : (uint32_t)r * 128u + (uint32_t)((pc ^ (r & 7)) << 4)),
+                             make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7])));
+              }
+            }
+          }
+          fence_proxy_async();          // generic-proxy writes of the staging tile -> visible to the TMA (async proxy)
+          named_bar_sync(1 + wg, 128);  // staging tile complete
+          if (r == 0) {
+            const int cb = spade ? ((n_base + colb) >> 1) : (n_base + colb);
+            tma_store_4d(tail ? &a.tmOutT : &a.tmOut, so, cb, tile_x0, tile_y0, tile_n0);
+            if (spade && a.gamma_out) tma_store_4d(tail ? &a.tmGamT : &a.tmGam, sg, cb, tile_x0, tile_y0, tile_n0);
+            bulk_commit();
+          }
+        }
+        if (!waited) {  // no slab of this tile was ours: stay in step with the accumulator ring before releasing it
+          mbar_wait_acct(bar_tfull(acc), aph, acct, w0);
+          tc_fence_after();
+        }
+      } else if (a.epi == 0) {
+        mbar_wait_acct(bar_tfull(acc), aph, acct, w0);
+        tc_fence_after();
         // ---------------- LINEAR
         const int store_c = (a.out_dtype == 0 && a.out_layout == 0) ? ((a.out_c + 7) & ~7) : a.out_c;
-        for (int col = wg * 16; col < a.BN; col += 16 * kEpiWG) {
+        for (int col = wg * 16; col < a.BN; col += 16 * kEpiC) {
           uint32_t v[16];
           __syncwarp();
           tmem_ld16(taddr + col, v);
@@ -382,77 +589,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
             }
           }
         }
-      } else {
-        // ---------------- SPADE: 16 GEMM columns = 8 channels of (gamma, beta)
-        const int sh0 = a.x0_shift;
-        const long long pix0 = ((long long)n * (a.Hout >> sh0) + (y >> sh0)) * (a.Wout >> sh0) + (x >> sh0);
-        const float nz = (valid && a.noise) ? __ldg(a.noise + pix) : 0.f;
-        for (int col = wg * 16; col < a.BN; col += 16 * kEpiWG) {
-          const int c0 = (n_base + col) >> 1;
-          const bool live = valid && c0 < a.C_mod;
-          // issue every global load of this chunk before touching TMEM so their latencies overlap the tcgen05.ld
-          uint4 xv = make_uint4(0, 0, 0, 0);
-          float mu[8], rs[8], nsv[8], sh[16];
-          if (live) {
-            const __nv_bfloat16* xp = (c0 < a.x0_c) ? (a.x0 + pix0 * a.x0_pitch + c0)
-                                                     : (a.x1 + pix * a.x1_pitch + (c0 - a.x0_c));
-            xv = __ldg(reinterpret_cast<const uint4*>(xp));
-            const float4* mp = reinterpret_cast<const float4*>(a.mean + (long long)n * a.C_mod + c0);
-            const float4* rp = reinterpret_cast<const float4*>(a.rstd + (long long)n * a.C_mod + c0);
-            *reinterpret_cast<float4*>(mu) = __ldg(mp);
-            *reinterpret_cast<float4*>(mu + 4) = __ldg(mp + 1);
-            *reinterpret_cast<float4*>(rs) = __ldg(rp);
-            *reinterpret_cast<float4*>(rs + 4) = __ldg(rp + 1);
-            if (a.noise_scale) {
-              const float4* np_ = reinterpret_cast<const float4*>(a.noise_scale + c0);
-              *reinterpret_cast<float4*>(nsv) = __ldg(np_);
-              *reinterpret_cast<float4*>(nsv + 4) = __ldg(np_ + 1);
-            } else {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) nsv[i] = 0.f;
-            }
-            if (a.shift) {
-              const float4* sp = reinterpret_cast<const float4*>(a.shift + 2 * c0);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(sh + 4 * i) = __ldg(sp + i);
-            } else {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) sh[i] = 0.f;
-            }
-          }
-          uint32_t v[16];
-          __syncwarp();
-          tmem_ld16(taddr + col, v);
-          tmem_wait_ld();
-          if (!live) continue;
-          const float xs[8] = {bf16_lo(xv.x), bf16_hi(xv.x), bf16_lo(xv.y), bf16_hi(xv.y),
-                               bf16_lo(xv.z), bf16_hi(xv.z), bf16_lo(xv.w), bf16_hi(xv.w)};
-          float o[8], gmv[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float xval = fmaf(nz, nsv[i], xs[i]);
-            const float gm = __uint_as_float(v[2 * i]) + sh[2 * i];
-            const float bt = __uint_as_float(v[2 * i + 1]) + sh[2 * i + 1];
-            const float xn = (xval - mu[i]) * rs[i];
-            gmv[i] = gm;
-            o[i] = apply_act(fmaf(xn, 1.f + gm, bt), a.act);
-          }
-          if (a.gamma_out) {  // training: keep gamma for the backward pass (saves re-running this GEMM)
-            uint4 gv;
-            gv.x = pack_bf16(gmv[0], gmv[1]); gv.y = pack_bf16(gmv[2], gmv[3]);
-            gv.z = pack_bf16(gmv[4], gmv[5]); gv.w = pack_bf16(gmv[6], gmv[7]);
-            *reinterpret_cast<uint4*>(a.gamma_out + pix * a.gamma_pitch + c0) = gv;
-          }
-          uint4 ov;
-          ov.x = pack_bf16(o[0], o[1]); ov.y = pack_bf16(o[2], o[3]);
-          ov.z = pack_bf16(o[4], o[5]); ov.w = pack_bf16(o[6], o[7]);
-          *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) + pix * a.out_pitch + c0) = ov;
-        }
-      }
+      }  // (the SPADE epilogue always writes bf16 NHWC: it only exists in the staged form above)
       __syncwarp();
       tc_fence_before();
       mbar_arrive(bar_tempty(acc));
       if (++acc == NACC) { acc = 0; aph ^= 1u; }
+    }
+    if (a.stage_out && r == 0) bulk_wait_read<0>();  // the last TMA store must have drained its staging tile before the CTA exits
+    if (acct && warp == 4 && lane == 0) {  // first epilogue warp: time stalled on the accumulator vs total
+      a.stats[blockIdx.x * 16 + 6] = w0;
+      a.stats[blockIdx.x * 16 + 7] = (unsigned long long)(clock64() - t_begin);
     }
   }
 
@@ -472,8 +618,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
 // The epilogue thread owns one output channel (a TMEM lane): scale/shift/activation per thread, then a bf16 transpose through
 // shared memory so that every pixel's channels leave as contiguous 16-byte vectors (coalesced stores).
 // Tap-by-tap loading, BK = 64, LINEAR epilogue, bf16 NHWC output without residual; everything else stays on conv_igemm_kernel.
-__device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
-
 template <int ACT>
 __device__ __forceinline__ float act_t(float v) {
   if (ACT == 1) return fmaxf(v, 0.f);
@@ -714,7 +858,7 @@ static int launch_conv(const ConvArgs& args, int grid, size_t smem, cudaStream_t
     if (e != cudaSuccess) return set_error(HRV_ECUDA, "cudaFuncSetAttribute(conv_igemm): %s", cudaGetErrorString(e));
     attr_done = true;
   }
-  conv_igemm_kernel<BK><<<grid, kThreads, smem, st>>>(args);
+  conv_igemm_kernel<BK><<<grid, kThreadsC, smem, st>>>(args);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(HRV_ECUDA, "conv_igemm launch: %s", cudaGetErrorString(e));
   return HRV_OK;
@@ -737,6 +881,15 @@ static int launch_pixn(const ConvArgs& args, int grid, size_t smem, cudaStream_t
 
 using namespace hrv;
 
+#ifndef HRV_F16
+// Debug hook of tools/conv_stall_probe.py (not part of the public header): subsequent bf16 convolutions on the classic kernel write
+// per-CTA stall counters (16 x u64 per CTA) into `buf` (device memory for >= sm_count CTAs); nullptr switches it off.
+static unsigned long long* g_conv_stats = nullptr;
+extern "C" void hrv_debug_set_conv_stats(void* buf) { g_conv_stats = (unsigned long long*)buf; }
+#else
+static unsigned long long* const g_conv_stats = nullptr;
+#endif
+
 extern "C" int hrv_conv2d_fwd(const hrv_conv_params* p, hrv_stream stream) {
   if (!p) return set_error(HRV_EINVAL, "conv: null params");
   const hrv_tensor& in = p->in;
@@ -757,6 +910,7 @@ extern "C" int hrv_conv2d_fwd(const hrv_conv_params* p, hrv_stream stream) {
   ConvArgs a;
   memset(&a, 0, sizeof(a));
   a.Nimg = out.n; a.Hout = out.h; a.Wout = out.w;
+  a.stats = g_conv_stats;
   // Pixel-N variant (weights as the M operand, 256 pixels as N): few output channels, plain bf16 NHWC output.
   const char* env_pixn = getenv("HRV_CONV_PIXN");  // read per call: tests flip it to compare the two kernels on identical inputs
   const bool pixn = !(env_pixn && env_pixn[0] == '0') && p->epi == HRV_EPI_LINEAR && p->bk == 64 && p->n_gemm <= 128 &&
@@ -811,11 +965,21 @@ extern "C" int hrv_conv2d_fwd(const hrv_conv_params* p, hrv_stream stream) {
     return set_error(HRV_EINVAL, "conv: unknown epilogue %d", p->epi);
   }
 
+  // ---- staged epilogue (classic kernel, bf16 NHWC output): per-warpgroup staging tiles + TMA stores
+  const bool stage_out = !pixn && out.dtype == HRV_BF16 && p->out_layout == HRV_NHWC;
+  uint32_t staging = 0;
+  if (stage_out) {
+    a.stage_out = 1;
+    a.epi_off = 2048u;
+    a.epi_buf_bytes = 128u * (p->epi == HRV_EPI_SPADE ? 64u : 128u);
+    a.epi_wg_bytes = a.epi_buf_bytes * ((p->epi == HRV_EPI_SPADE && p->gamma_out.ptr) ? 2u : 1u);
+    staging = (uint32_t)kEpiC * a.epi_wg_bytes;
+  }
   // ---- pipeline geometry
   const int elem = 2;
   const int taps = p->kh * p->kw;
   const uint32_t row_bytes = p->bk * 2;
-  const uint32_t budget = 225u * 1024u - 3072u;  // 1 KB alignment slack + 2 KB control block
+  const uint32_t budget = 225u * 1024u - 3072u - staging;  // 1 KB alignment slack + 2 KB control block + epilogue staging
   const int LP = TW + p->kw - 1, HRows = (TH + p->kh - 1) * LP;
   int tpb = 1;
   if (halo) {
@@ -825,16 +989,21 @@ extern "C" int hrv_conv2d_fwd(const hrv_conv_params* p, hrv_stream stream) {
     a.a_stage_bytes = (int)((HRows * row_bytes + 1023u) & ~1023u);
     static const char* env_tpb = getenv("HRV_CONV_TPB_KB");
     const uint32_t tpb_cap = (env_tpb ? (uint32_t)atoi(env_tpb) : 80u) * 1024u;
-    for (int d = taps; d >= 1; --d)
-      if (taps % d == 0 && (uint32_t)d * p->bn * row_bytes <= tpb_cap) { tpb = d; break; }
-    a.tpb = tpb;
-    a.b_stage_bytes = (int)(((uint32_t)tpb * p->bn * row_bytes + 1023u) & ~1023u);
     // halo ring: ~72 KB in flight (at least 3 stages), the rest of shared memory goes to the weight ring
     int sa = (int)(72u * 1024u / (uint32_t)a.a_stage_bytes);
     if (sa < 3) sa = 3;
     if (sa > 16) sa = 16;
     static const char* env_sa = getenv("HRV_CONV_SA");
     if (env_sa) sa = atoi(env_sa);
+    // taps per weight TMA: the largest divisor of the tap count whose stage is <= tpb_cap and still leaves >= 3 weight stages
+    // (>= 2 as a last resort) next to the halo ring
+    for (int want = 3; want >= 2 && tpb == 1; --want)
+      for (int d = taps; d >= 1; --d) {
+        const uint32_t bs = ((uint32_t)d * p->bn * row_bytes + 1023u) & ~1023u;
+        if (taps % d == 0 && (uint32_t)d * p->bn * row_bytes <= tpb_cap && (uint32_t)sa * a.a_stage_bytes + (uint32_t)want * bs <= budget) { tpb = d; break; }
+      }
+    a.tpb = tpb;
+    a.b_stage_bytes = (int)(((uint32_t)tpb * p->bn * row_bytes + 1023u) & ~1023u);
     while (sa > 2 && (uint32_t)sa * a.a_stage_bytes + 2u * a.b_stage_bytes > budget) --sa;
     int sb = (int)((budget - (uint32_t)sa * a.a_stage_bytes) / (uint32_t)a.b_stage_bytes);
     if (sb > kMaxStages) sb = kMaxStages;
@@ -868,6 +1037,30 @@ extern "C" int hrv_conv2d_fwd(const hrv_conv_params* p, hrv_stream stream) {
     int rc = encode_tensor_map(&a.tmB, 3, const_cast<void*>(p->wpack), dims, strides, box, es, sw);
     if (rc) return rc;
   }
+  if (stage_out) {
+    const bool sp = p->epi == HRV_EPI_SPADE;
+    const CUtensorMapSwizzle osw = sp ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+    cuuint32_t box[4] = {(cuuint32_t)(sp ? 32 : 64), (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TN};
+    a.tail_cols = p->bn % 64;
+    cuuint32_t tbox[4] = {(cuuint32_t)(sp ? a.tail_cols / 2 : a.tail_cols), (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TN};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    {
+      cuuint64_t dims[4] = {(cuuint64_t)((out.c + 7) & ~7), (cuuint64_t)out.w, (cuuint64_t)out.h, (cuuint64_t)out.n};
+      cuuint64_t strides[3] = {(cuuint64_t)out.pitch * elem, (cuuint64_t)out.w * out.pitch * elem, (cuuint64_t)out.h * out.w * out.pitch * elem};
+      int rc = encode_tensor_map(&a.tmOut, 4, out.ptr, dims, strides, box, es, osw);
+      if (rc) return rc;
+      if (a.tail_cols && (rc = encode_tensor_map(&a.tmOutT, 4, out.ptr, dims, strides, tbox, es, CU_TENSOR_MAP_SWIZZLE_NONE))) return rc;
+    }
+    if (sp && p->gamma_out.ptr) {
+      const hrv_tensor& g = p->gamma_out;
+      if (g.n != out.n || g.h != out.h || g.w != out.w) return set_error(HRV_EINVAL, "conv(spade): gamma_out extent mismatch");
+      cuuint64_t dims[4] = {(cuuint64_t)((g.c + 7) & ~7), (cuuint64_t)g.w, (cuuint64_t)g.h, (cuuint64_t)g.n};
+      cuuint64_t strides[3] = {(cuuint64_t)g.pitch * elem, (cuuint64_t)g.w * g.pitch * elem, (cuuint64_t)g.h * g.w * g.pitch * elem};
+      int rc = encode_tensor_map(&a.tmGam, 4, g.ptr, dims, strides, box, es, osw);
+      if (rc) return rc;
+      if (a.tail_cols && (rc = encode_tensor_map(&a.tmGamT, 4, g.ptr, dims, strides, tbox, es, CU_TENSOR_MAP_SWIZZLE_NONE))) return rc;
+    }
+  }
   cudaStream_t st = (cudaStream_t)stream;
   if (pixn) {
     a.tiles_m = a.tiles_x * a.tiles_y * a.tiles_img;
@@ -883,7 +1076,7 @@ extern "C" int hrv_conv2d_fwd(const hrv_conv_params* p, hrv_stream stream) {
     if (a.pairs < gridp) gridp = a.pairs;
     return launch_pixn(a, gridp, smem_p, st);
   }
-  size_t smem = 3072 + (halo ? (size_t)a.stages * a.a_stage_bytes + (size_t)a.sb_stages * a.b_stage_bytes
+  size_t smem = 3072 + staging + (halo ? (size_t)a.stages * a.a_stage_bytes + (size_t)a.sb_stages * a.b_stage_bytes
                              : (size_t)a.stages * (128 * row_bytes + (((uint32_t)p->bn * row_bytes + 1023u) & ~1023u)));
   if (smem < 120 * 1024) smem = 120 * 1024;  // force one CTA per SM (TMEM: up to 512 columns per CTA)
 

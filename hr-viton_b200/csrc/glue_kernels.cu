@@ -132,6 +132,8 @@ struct ParseArgs {
   const float* seg;
   long long* idx;
   float* onehot;
+  float* overlap;       // optional (n,1,H,W): sum over the classes in occl_mask of softmax_c(blurred scores)  (remove_overlap's operand)
+  unsigned occl_mask;
   int n, C, h, w, H, W, groups;
   float sy, sx;
   float g[15];
@@ -145,6 +147,7 @@ __global__ void __launch_bounds__(256) parse_blur_argmax_kernel(const __grid_con
   const int col = tid & 31, rq = tid >> 5;  // thread owns output rows rq, rq+8, rq+16, rq+24 of column col
   float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
   int arg[4] = {0, 0, 0, 0};
+  float sm_all[4] = {0.f, 0.f, 0.f, 0.f}, sm_sel[4] = {0.f, 0.f, 0.f, 0.f};  // online softmax sums relative to the running maximum `best`
   for (int c = 0; c < a.C; ++c) {
     const float* s = a.seg + ((long long)n * a.C + c) * a.h * a.w;
     for (int i = tid; i < kU * kU; i += 256) {
@@ -176,6 +179,12 @@ __global__ void __launch_bounds__(256) parse_blur_argmax_kernel(const __grid_con
       float acc = 0.f;
 #pragma unroll
       for (int k = 0; k < 15; ++k) acc = fmaf(a.g[k], Hb[y + k][col], acc);
+      if (a.overlap) {  // softmax over classes without storing the blurred planes: rescale the sums when the maximum moves
+        const float m_new = fmaxf(best[j], acc);
+        const float scale = __expf(best[j] - m_new), e = __expf(acc - m_new);
+        sm_all[j] = sm_all[j] * scale + e;
+        sm_sel[j] = sm_sel[j] * scale + (((a.occl_mask >> c) & 1u) ? e : 0.f);
+      }
       if (acc > best[j]) { best[j] = acc; arg[j] = c; }
     }
     // U / Hb are rewritten by the next channel: the barrier after the U fill separates Hb readers from Hb writers,
@@ -187,6 +196,7 @@ __global__ void __launch_bounds__(256) parse_blur_argmax_kernel(const __grid_con
     if (Y < a.H && X < a.W) {
       const long long p = ((long long)n * a.H + Y) * a.W + X;
       if (a.idx) a.idx[p] = arg[j];
+      if (a.overlap) a.overlap[p] = sm_sel[j] / sm_all[j];
       if (a.onehot) {
         const int grp = a.group_of[arg[j]];
         for (int q = 0; q < a.groups; ++q) a.onehot[(((long long)n * a.groups + q) * a.H + Y) * a.W + X] = (q == grp) ? 1.f : 0.f;
@@ -243,7 +253,9 @@ __global__ void __launch_bounds__(256) gaussian_blur_kernel(const __grid_constan
 __global__ void __launch_bounds__(256) flow_warp_nchw_kernel(const float* __restrict__ flow_lo, int hl, int wl, const float* __restrict__ lin_x,
                                                             const float* __restrict__ lin_y, const float* __restrict__ src, int C, int Hs, int Ws,
                                                             float* __restrict__ dst, int H, int W, float div_x, float div_y, float sc_y,
-                                                            float sc_x, float* __restrict__ grid_out, long long npix) {
+                                                            float sc_x, float* __restrict__ grid_out, const float* __restrict__ mask_src,
+                                                            const float* __restrict__ overlap, float* __restrict__ mask_out, int composite,
+                                                            long long npix) {
   const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (pix >= npix) return;
   const int x = (int)(pix % W), y = (int)((pix / W) % H), n = (int)(pix / ((long long)W * H));
@@ -275,11 +287,33 @@ __global__ void __launch_bounds__(256) flow_warp_nchw_kernel(const float* __rest
   const float wx0 = 1.f - tx, wy0 = 1.f - ty;
   const float w00 = wy0 * wx0, w01 = wy0 * wx1, w10 = wy1 * wx0, w11 = wy1 * wx1;
   const long long plane_s = (long long)Hs * Ws, plane_d = (long long)H * W;
+  const long long o00 = (long long)sy0 * Ws + sx0, o01 = (long long)sy0 * Ws + sx1, o10 = (long long)sy1 * Ws + sx0, o11 = (long long)sy1 * Ws + sx1;
+  float wm = 1.f;
+  if (mask_src) {  // the cloth mask rides along: warped with the same taps, occlusion-corrected, optionally composited into the cloth
+    const float* mp = mask_src + (long long)n * plane_s;
+    wm = __ldg(mp + o00) * w00 + __ldg(mp + o01) * w01 + __ldg(mp + o10) * w10 + __ldg(mp + o11) * w11;
+    if (overlap) wm = wm - __ldg(overlap + pix) * wm;  // remove_overlap (train_generator.py:26-31, test_generator.py:19-24)
+    if (mask_out) mask_out[pix] = wm;
+  }
   const float* sp = src + (long long)n * C * plane_s;
   float* dp = dst + (long long)n * C * plane_d + (long long)y * W + x;
-  for (int c = 0; c < C; ++c, sp += plane_s, dp += plane_d)
-    *dp = __ldg(sp + (long long)sy0 * Ws + sx0) * w00 + __ldg(sp + (long long)sy0 * Ws + sx1) * w01 + __ldg(sp + (long long)sy1 * Ws + sx0) * w10 +
-          __ldg(sp + (long long)sy1 * Ws + sx1) * w11;
+  for (int c = 0; c < C; ++c, sp += plane_s, dp += plane_d) {
+    float v = __ldg(sp + o00) * w00 + __ldg(sp + o01) * w01 + __ldg(sp + o10) * w10 + __ldg(sp + o11) * w11;
+    if (composite) v = v * wm + (1.f - wm);  // warped_cloth * mask + white * (1 - mask)  (train_generator.py:244, test_generator.py:178)
+    *dp = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- label map -> one-hot planes
+// Input feeding (cp_dataset.py:150-172 builds the 13-channel one-hot parse map on the CPU and ships it as fp32):
+// the host ships ONE byte per pixel, this kernel expands it on the device.  out[n,c,p] = (label[n,p] == c).  thread = pixel.
+__global__ void __launch_bounds__(256) onehot_u8_kernel(const unsigned char* __restrict__ lab, float* __restrict__ out, int C, long long hw, long long npix) {
+  const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= npix) return;
+  const long long n = pix / hw, p = pix - n * hw;
+  const int l = (int)__ldg(lab + pix);
+  float* o = out + n * C * hw + p;
+  for (int c = 0; c < C; ++c) o[(long long)c * hw] = (c == l) ? 1.f : 0.f;
 }
 
 // ---------------------------------------------------------------------------------------------- im2col for tiny-Cin convolutions
@@ -440,13 +474,14 @@ extern "C" int hrv_avgpool3s2_bwd(const hrv_tensor* dy, const hrv_tensor* dx, hr
 }
 
 extern "C" int hrv_parse_blur_argmax(const float* seg, int32_t n, int32_t c, int32_t h, int32_t w, int32_t H, int32_t W,
-                                     const int32_t* group_of, int32_t groups, int64_t* idx, float* onehot, hrv_stream stream) {
-  if (!seg || (!idx && !onehot) || n < 1 || c < 1 || c > 32 || h < 1 || w < 1 || H < 1 || W < 1)
+                                     const int32_t* group_of, int32_t groups, int64_t* idx, float* onehot, uint32_t occl_mask,
+                                     float* overlap, hrv_stream stream) {
+  if (!seg || (!idx && !onehot && !overlap) || n < 1 || c < 1 || c > 32 || h < 1 || w < 1 || H < 1 || W < 1)
     return set_error(HRV_EINVAL, "parse_blur_argmax: bad arguments (c must be <= 32)");
   if (onehot && (!group_of || groups < 1)) return set_error(HRV_EINVAL, "parse_blur_argmax: onehot needs group_of / groups");
   ParseArgs a;
   memset(&a, 0, sizeof(a));
-  a.seg = seg; a.idx = (long long*)idx; a.onehot = onehot;
+  a.seg = seg; a.idx = (long long*)idx; a.onehot = onehot; a.overlap = overlap; a.occl_mask = occl_mask;
   a.n = n; a.C = c; a.h = h; a.w = w; a.H = H; a.W = W; a.groups = groups;
   a.sy = (float)h / (float)H; a.sx = (float)w / (float)W;
   double g[15], sum = 0;
@@ -462,6 +497,13 @@ extern "C" int hrv_parse_blur_argmax(const float* seg, int32_t n, int32_t c, int
   dim3 grid((W + kTile - 1) / kTile, (H + kTile - 1) / kTile, n);
   parse_blur_argmax_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
   return launched("parse_blur_argmax");
+}
+
+extern "C" int hrv_onehot_u8(const uint8_t* labels, int32_t n, int32_t classes, int32_t h, int32_t w, float* out, hrv_stream stream) {
+  if (!labels || !out || n < 1 || classes < 1 || h < 1 || w < 1) return set_error(HRV_EINVAL, "onehot_u8: bad arguments");
+  const long long hw = (long long)h * w, npix = hw * n;
+  onehot_u8_kernel<<<nblocks(npix, 256), 256, 0, (cudaStream_t)stream>>>(labels, out, classes, hw, npix);
+  return launched("onehot_u8");
 }
 
 extern "C" int hrv_gaussian_blur(const float* src, int32_t planes, int32_t h, int32_t w, int32_t ksize, float sigma, float* dst,
@@ -481,12 +523,15 @@ extern "C" int hrv_gaussian_blur(const float* src, int32_t planes, int32_t h, in
 
 extern "C" int hrv_flow_warp_nchw(const float* flow_lo, int32_t n, int32_t hl, int32_t wl, const float* lin_x, const float* lin_y,
                                   const float* src, int32_t c, int32_t hs, int32_t ws, float* dst, int32_t h, int32_t w, float div_x,
-                                  float div_y, float* grid_out, hrv_stream stream) {
+                                  float div_y, float* grid_out, const float* mask_src, const float* overlap, float* mask_out,
+                                  int32_t composite, hrv_stream stream) {
   if (!flow_lo || !lin_x || !lin_y || !src || !dst || n < 1 || hl < 1 || wl < 1 || c < 1 || hs < 1 || ws < 1 || h < 1 || w < 1)
     return set_error(HRV_EINVAL, "flow_warp_nchw: bad arguments");
+  if ((overlap || mask_out || composite) && !mask_src) return set_error(HRV_EINVAL, "flow_warp_nchw: overlap / mask_out / composite need mask_src");
   const long long npix = (long long)n * h * w;
   flow_warp_nchw_kernel<<<nblocks(npix, 256), 256, 0, (cudaStream_t)stream>>>(flow_lo, hl, wl, lin_x, lin_y, src, c, hs, ws, dst, h, w, div_x,
-                                                                             div_y, (float)hl / (float)h, (float)wl / (float)w, grid_out, npix);
+                                                                             div_y, (float)hl / (float)h, (float)wl / (float)w, grid_out, mask_src,
+                                                                             overlap, mask_out, composite, npix);
   return launched("flow_warp_nchw");
 }
 

@@ -28,3 +28,5 @@
 #define hrv_l1_bwd hrv_l1_bwd_f16
 #define hrv_gaussian_blur hrv_gaussian_blur_f16
 #define hrv_flow_warp_nchw hrv_flow_warp_nchw_f16
+#define hrv_instnorm_stats2 hrv_instnorm_stats2_f16
+#define hrv_onehot_u8 hrv_onehot_u8_f16

@@ -301,6 +301,27 @@ def instnorm_stats(x0, x0_shift, x1, h, w, noise, noise_scale, eps=1e-5):
     return mean, rstd
 
 
+def instnorm_stats2(x0, x0_shift, x1, h, w, noises, noise_scales, eps=1e-5):
+    """Statistics of one or two SPADE norms sharing the input cat(up2^shift(x0), x1) (hrv_instnorm_stats2): `noises` / `noise_scales`
+    are lists of 1 or 2 entries (a noise entry may be None).  Returns [(mean, rstd), ...] in the same order."""
+    n = x0.n
+    c = x0.c + (x1.c if x1 is not None else 0)
+    k = len(noises)
+    assert k in (1, 2) and len(noise_scales) == k
+    dev = x0.buf.device
+    outs = [(torch.empty((n, c), dtype=torch.float32, device=dev), torch.empty((n, c), dtype=torch.float32, device=dev)) for _ in range(k)]
+    ws = _workspace((n * c * 4 + n * 4) * 8, dev)
+    t0 = x0.ct()
+    t1 = x1.ct() if x1 is not None else _NULL
+    src_bytes = 2.0 * n * (x0.h * x0.w * x0.c + (h * w * x1.c if x1 is not None else 0)) + 4.0 * n * h * w * sum(z is not None for z in noises)
+    nz1, ns1, m1, r1 = (noises[1], noise_scales[1], outs[1][0], outs[1][1]) if k == 2 else (None, None, None, None)
+    with _Timed("instnorm_stats", src_bytes, launches=3 + (1 if x1 is not None else 0), label="c%d n%d %dx%d shift%d norms%d" % (c, n, h, w, x0_shift, k)):
+        capi.check(_L(x0).hrv_instnorm_stats2(ctypes.byref(t0), x0_shift, ctypes.byref(t1), h, w, _p(noises[0]), _p(noise_scales[0]), _p(nz1), _p(ns1),
+                                              eps, outs[0][0].data_ptr(), outs[0][1].data_ptr(), _p(m1), _p(r1), ws.data_ptr(), ws.numel(), _stream()),
+                   "instnorm_stats2")
+    return outs
+
+
 def instnorm_apply(x, mean, rstd, act, out=None):
     out = x if out is None else out
     tx, ty = x.ct(), out.ct()
@@ -381,8 +402,9 @@ def l1_bwd(a, b, gscale):
     return da
 
 
-def parse_blur_argmax(seg, size, group_of=None, groups=0, want_idx=True):
-    """seg (n,c,h,w) fp32 cuda -> (idx (n,1,H,W) int64 | None, onehot (n,groups,H,W) fp32 | None); hrv_parse_blur_argmax."""
+def parse_blur_argmax(seg, size, group_of=None, groups=0, want_idx=True, overlap_classes=None):
+    """seg (n,c,h,w) fp32 cuda -> (idx (n,1,H,W) int64 | None, onehot (n,groups,H,W) fp32 | None[, overlap (n,1,H,W)]);
+    hrv_parse_blur_argmax.  overlap_classes: class ids whose softmax (over the blurred scores) is summed into `overlap`."""
     assert seg.is_cuda and seg.dtype == torch.float32
     seg = seg.contiguous()
     n, c, h, w = seg.shape
@@ -390,10 +412,28 @@ def parse_blur_argmax(seg, size, group_of=None, groups=0, want_idx=True):
     idx = torch.empty((n, 1, H, W), dtype=torch.int64, device=seg.device) if want_idx else None
     onehot = torch.empty((n, groups, H, W), dtype=torch.float32, device=seg.device) if group_of is not None else None
     garr = (ctypes.c_int32 * c)(*group_of) if group_of is not None else None
+    overlap = torch.empty((n, 1, H, W), dtype=torch.float32, device=seg.device) if overlap_classes else None
+    mask = 0
+    for k in (overlap_classes or ()):
+        mask |= 1 << int(k)
     with _Timed("glue", 0.0, label="parse_blur_argmax"):
-        capi.check(capi.lib().hrv_parse_blur_argmax(seg.data_ptr(), n, c, h, w, H, W, garr, groups, _p(idx), _p(onehot), _stream()),
+        capi.check(capi.lib().hrv_parse_blur_argmax(seg.data_ptr(), n, c, h, w, H, W, garr, groups, _p(idx), _p(onehot), mask, _p(overlap), _stream()),
                    "parse_blur_argmax")
-    return idx, onehot
+    return (idx, onehot, overlap) if overlap_classes else (idx, onehot)
+
+
+def onehot_u8(labels, classes, out=None):
+    """(N,1,H,W) or (N,H,W) uint8 label map (cuda) -> (N,classes,H,W) fp32 one-hot planes (hrv_onehot_u8): the device half of the
+    input feeding — the host ships one byte per pixel instead of `classes` floats (cp_dataset.py:150-172)."""
+    assert labels.is_cuda and labels.dtype == torch.uint8
+    labels = labels.contiguous()
+    n, h, w = labels.shape[0], labels.shape[-2], labels.shape[-1]
+    if out is None:
+        out = torch.empty((n, classes, h, w), dtype=torch.float32, device=labels.device)
+    assert out.is_contiguous() and out.shape == (n, classes, h, w)
+    with _Timed("glue", 0.0, label="onehot_u8"):
+        capi.check(capi.lib().hrv_onehot_u8(labels.data_ptr(), n, classes, h, w, out.data_ptr(), _stream()), "onehot_u8")
+    return out
 
 
 def gaussian_blur(x, ksize=15, sigma=3.0):
@@ -407,10 +447,12 @@ def gaussian_blur(x, ksize=15, sigma=3.0):
     return out
 
 
-def flow_warp_nchw(flow_lo, src, size, div_xy, want_grid=False):
+def flow_warp_nchw(flow_lo, src, size, div_xy, want_grid=False, mask=None, overlap=None, composite=False):
     """The hi-res cloth warp of the glue (train_generator.py:232-238): flow_lo fp32 (N,hl,wl,2) is up-sampled bilinearly to `size`,
     divided by div_xy, added to the linspace base grid and used to grid_sample (bilinear, border) src fp32 (N,C,Hs,Ws).
-    Returns (warped (N,C,H,W) fp32, grid (N,H,W,2) | None)."""
+    mask (N,1,Hs,Ws): the cloth mask is warped with the same taps (returned third), `overlap` (N,1,H,W) applies remove_overlap to it and
+    composite=True blends the cloth over white with it (train_generator.py:239-244).
+    Returns (warped (N,C,H,W) fp32, grid (N,H,W,2) | None[, warped mask (N,1,H,W)])."""
     assert flow_lo.is_cuda and src.is_cuda and flow_lo.dtype == torch.float32 and src.dtype == torch.float32
     flow_lo, src = flow_lo.contiguous(), src.contiguous()
     n, hl, wl, _ = flow_lo.shape
@@ -419,11 +461,19 @@ def flow_warp_nchw(flow_lo, src, size, div_xy, want_grid=False):
     dev = src.device
     out = torch.empty((n, c, H, W), dtype=torch.float32, device=dev)
     grid = torch.empty((n, H, W, 2), dtype=torch.float32, device=dev) if want_grid else None
+    mask_out = None
+    if mask is not None:
+        mask = mask.float().contiguous()
+        assert mask.shape == (n, 1, hs, ws)
+        mask_out = torch.empty((n, 1, H, W), dtype=torch.float32, device=dev)
+    if overlap is not None:
+        overlap = overlap.contiguous()
+        assert overlap.shape == (n, 1, H, W) and overlap.dtype == torch.float32
     with _Timed("glue", 0.0, label="flow_warp_nchw"):
         capi.check(capi.lib().hrv_flow_warp_nchw(flow_lo.data_ptr(), n, hl, wl, linspace_table(W, dev).data_ptr(), linspace_table(H, dev).data_ptr(),
                                                  src.data_ptr(), c, hs, ws, out.data_ptr(), H, W, float(div_xy[0]), float(div_xy[1]), _p(grid),
-                                                 _stream()), "flow_warp_nchw")
-    return out, grid
+                                                 _p(mask), _p(overlap), _p(mask_out), 1 if composite else 0, _stream()), "flow_warp_nchw")
+    return (out, grid, mask_out) if mask is not None else (out, grid)
 
 
 def avgpool3s2(x):

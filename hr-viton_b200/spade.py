@@ -212,11 +212,11 @@ class SPADEResBlock(nn.Module):
         return self._cache
 
     @staticmethod
-    def _spade(pk, actv, x0, x0_shift, x1, noise, act):
+    def _spade(pk, actv, x0, x0_shift, x1, noise, act, stats=None):
         """act(InstanceNorm(x + noise*ns) * (1 + gamma(actv)) + beta(actv)) for the virtual tensor cat(up(x0), x1)."""
         gb, gb_b, ns = pk
         n, h, w = actv.n, actv.h, actv.w
-        mean, rstd = ops.instnorm_stats(x0, x0_shift, x1, h, w, noise, ns)
+        mean, rstd = stats if stats is not None else ops.instnorm_stats2(x0, x0_shift, x1, h, w, [noise], [ns])[0]
         c = x0.c + (x1.c if x1 is not None else 0)
         return ops.conv2d_spade(actv, gb, Act.empty(n, h, w, c), x0, x0_shift, x1, mean, rstd, noise, ns, gb_b, act)
 
@@ -237,13 +237,17 @@ class SPADEResBlock(nn.Module):
             actv = ops.conv2d(seg, p["shared"], Act.empty(n, h, w, p["shared"].n_gemm), act=ACT_RELU, shift=p["shared_b"])
         k = 0
         if self.learned_shortcut:
-            hs = self._spade(p["ns"], actv.slice(0, 128), x0, x0_shift, x1, noise_fn(n, h, w), ACT_NONE)
+            # norm_s and norm_0 normalise the same x with their own noise: one pass over the source tensors yields both statistics
+            nz_s, nz_0 = noise_fn(n, h, w), noise_fn(n, h, w)
+            st_s, st_0 = ops.instnorm_stats2(x0, x0_shift, x1, h, w, [nz_s, nz_0], [p["ns"][2], p["n0"][2]])
+            hs = self._spade(p["ns"], actv.slice(0, 128), x0, x0_shift, x1, nz_s, ACT_NONE, stats=st_s)
             x_s = ops.conv2d(hs, p["cs"], Act.empty(n, h, w, p["cs"].n_gemm))
             k = 128
+            h0 = self._spade(p["n0"], actv.slice(k, 128), x0, x0_shift, x1, nz_0, ACT_LRELU, stats=st_0)
         else:
             assert x0_shift == 0 and x1 is None
             x_s = x0
-        h0 = self._spade(p["n0"], actv.slice(k, 128), x0, x0_shift, x1, noise_fn(n, h, w), ACT_LRELU)
+            h0 = self._spade(p["n0"], actv.slice(k, 128), x0, x0_shift, x1, noise_fn(n, h, w), ACT_LRELU)
         dx = ops.conv2d(h0, p["c0"], Act.empty(n, h, w, p["c0"].n_gemm), shift=p["b0"])
         h1 = self._spade(p["n1"], actv.slice(k + 128, 128), dx, 0, None, noise_fn(n, h, w), ACT_LRELU)
         return ops.conv2d(h1, p["c1"], Act.empty(n, h, w, p["c1"].n_gemm), shift=p["b1"], res=x_s, act=out_act)

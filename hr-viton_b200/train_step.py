@@ -10,6 +10,7 @@ import torch.nn.functional as F
 _GRID_CACHE = {}
 LABELS7 = [[0], [2, 4, 7, 8, 9, 10, 11], [3], [1], [5], [6], [12]]  # train_generator.py:261-269
 GROUP_OF_13 = [next(i for i, grp in enumerate(LABELS7) if k in grp) for k in range(13)]
+OCCLUSION_CLASSES = [1, 2, 5, 6, 7, 8, 9, 10, 11, 12]  # remove_overlap: seg_out[:, 1:3] and seg_out[:, 5:] (train_generator.py:26-31)
 
 
 def gaussian_blur_15_3(x):
@@ -52,33 +53,99 @@ def make_generator_inputs(tocg, batch, fine_h, fine_w, occlusion=False, unfused_
             warped_cloth = F.grid_sample(c_paired, warped_grid, padding_mode="border", align_corners=False)
             warped_clothmask = F.grid_sample(cm, warped_grid, padding_mode="border", align_corners=False)
         else:
-            # flow up-sampling (x8) + normalisation + base grid + grid_sample of cloth and mask (train_generator.py:232-238): one kernel
-            # per source (hrv_flow_warp_nchw), no (N,H,W,2) grid / flow tensors in HBM
+            # product path: parse post-processing in one kernel (bilinear resize -> 15x15 Gaussian -> argmax -> one-hot -> 13->7 regroup,
+            # plus, under --occlusion, the softmax-overlap plane), then the hi-res warp of cloth + mask (flow x8 up-sampling, normalise,
+            # base grid, grid_sample, remove_overlap, white composite) in one kernel: no (N,H,W,2) grid, no 13 blurred planes in HBM
             from . import ops
             div = ((96 - 1.0) / 2.0, (128 - 1.0) / 2.0)
-            warped_cloth, _ = ops.flow_warp_nchw(flow_list[-1], c_paired.float(), (ih, iw), div)
-            warped_clothmask, _ = ops.flow_warp_nchw(flow_list[-1], cm.float(), (ih, iw), div)
-        if occlusion or unfused_parse:
-            fake_parse_gauss = gaussian_blur_15_3(F.interpolate(fake_segmap, size=(ih, iw), mode="bilinear"))
-            fake_parse = fake_parse_gauss.argmax(dim=1)[:, None]
             if occlusion:
-                so = F.softmax(fake_parse_gauss, dim=1)
-                warped_clothmask = warped_clothmask - torch.cat([so[:, 1:3], so[:, 5:]], 1).sum(1, keepdim=True) * warped_clothmask
-                warped_cloth = warped_cloth * warped_clothmask + (1 - warped_clothmask)
-            old_parse = torch.zeros(n, 13, fine_h, fine_w, device=cm.device).scatter_(1, fake_parse, 1.0)
-            mkey = ("regroup", str(cm.device))
-            if mkey not in _GRID_CACHE:  # 13 -> 7 class regrouping as a constant 7x13 0/1 matrix (train_generator.py:261-273)
-                m = torch.zeros(7, 13)
-                for i, idx in enumerate(LABELS7):
-                    m[i, idx] = 1.0
-                _GRID_CACHE[mkey] = m.to(cm.device)
-            parse = torch.einsum("ij,njhw->nihw", _GRID_CACHE[mkey], old_parse)
-        else:
-            # bilinear resize -> 15x15 Gaussian -> argmax -> one-hot -> 13->7 regroup (train_generator.py:247-273) in one kernel
-            from . import ops
-            _, parse = ops.parse_blur_argmax(fake_segmap.float(), (ih, iw), group_of=GROUP_OF_13, groups=7, want_idx=False)
+                _, parse, overlap = ops.parse_blur_argmax(fake_segmap.float(), (ih, iw), group_of=GROUP_OF_13, groups=7, want_idx=False,
+                                                          overlap_classes=OCCLUSION_CLASSES)
+                warped_cloth, _, warped_clothmask = ops.flow_warp_nchw(flow_list[-1], c_paired.float(), (ih, iw), div, mask=cm, overlap=overlap,
+                                                                       composite=True)
+            else:
+                _, parse = ops.parse_blur_argmax(fake_segmap.float(), (ih, iw), group_of=GROUP_OF_13, groups=7, want_idx=False)
+                warped_cloth, _ = ops.flow_warp_nchw(flow_list[-1], c_paired.float(), (ih, iw), div)
+            g_in = torch.cat((batch["agnostic"], batch["densepose"], warped_cloth), 1)
+            return g_in.detach(), parse.detach()
+        # ---- reference formulation with separate torch ops (CPU oracle pipeline of the tests; unfused_parse=True)
+        fake_parse_gauss = gaussian_blur_15_3(F.interpolate(fake_segmap, size=(ih, iw), mode="bilinear"))
+        fake_parse = fake_parse_gauss.argmax(dim=1)[:, None]
+        if occlusion:
+            so = F.softmax(fake_parse_gauss, dim=1)
+            warped_clothmask = warped_clothmask - torch.cat([so[:, 1:3], so[:, 5:]], 1).sum(1, keepdim=True) * warped_clothmask
+            warped_cloth = warped_cloth * warped_clothmask + (1 - warped_clothmask)
+        old_parse = torch.zeros(n, 13, fine_h, fine_w, device=cm.device).scatter_(1, fake_parse, 1.0)
+        mkey = ("regroup", str(cm.device))
+        if mkey not in _GRID_CACHE:  # 13 -> 7 class regrouping as a constant 7x13 0/1 matrix (train_generator.py:261-273)
+            m = torch.zeros(7, 13)
+            for i, idx in enumerate(LABELS7):
+                m[i, idx] = 1.0
+            _GRID_CACHE[mkey] = m.to(cm.device)
+        parse = torch.einsum("ij,njhw->nihw", _GRID_CACHE[mkey], old_parse)
         g_in = torch.cat((batch["agnostic"], batch["densepose"], warped_cloth), 1)
     return g_in.detach(), parse.detach()
+
+
+def _attach_reducers(reducers):
+    """Data-parallel gradient exchange of the bundled trainers: by default the reducers' hooks launch each bucket's all-reduce as soon
+    as its last gradient exists (overlapping the rest of backward()); HRV_DDP_MODE=explicit reduces after backward() instead.
+    Returns True when the step has to call reduce() itself."""
+    import os
+    if os.environ.get("HRV_DDP_MODE", "hooks") == "explicit":
+        return True
+    for r in reducers.values():
+        r.attach()
+    return False
+
+
+class BatchFeeder:
+    """Input feeding (cp_dataset.py:404-426 hands the loop one CPU batch per step): pinned host tensors travel on a
+    COPY stream into one of two device staging slots while the previous step still computes; one-hot maps (13-channel parse maps, half
+    of the batch's bytes as fp32) travel as ONE byte per pixel and are expanded on the device (hrv_onehot_u8).  consume() hands the
+    staged batch to the step as fp32 tensors (the graph's static inputs, or a per-step dict)."""
+    ONEHOT = ("parse_agnostic", "parse")
+
+    def __init__(self, batch_cpu, device):
+        self.device = device
+        self.host, self.classes = {}, {}
+        for k, v in batch_cpu.items():
+            if k in self.ONEHOT and v.dim() == 4 and v.shape[1] > 1:
+                self.classes[k] = v.shape[1]
+                self.host[k] = v.argmax(1, keepdim=True).to(torch.uint8).contiguous().pin_memory()
+            else:
+                self.host[k] = v.contiguous().pin_memory()
+        self.slots = [{k: torch.empty(v.shape, dtype=v.dtype, device=device) for k, v in self.host.items()} for _ in range(2)]
+        self.copy_stream = torch.cuda.Stream(device)
+        self.ready = [torch.cuda.Event(), torch.cuda.Event()]
+        self.free = [torch.cuda.Event(), torch.cuda.Event()]
+        self.bytes_per_step = int(sum(v.numel() * v.element_size() for v in self.host.values()))
+        self.slot = 0
+
+    def prefetch(self, slot=None):
+        slot = self.slot if slot is None else slot
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.free[slot])  # the step that consumed this slot last has read it
+            for k, v in self.host.items():
+                self.slots[slot][k].copy_(v, non_blocking=True)
+            self.ready[slot].record(self.copy_stream)
+
+    def consume(self, out):
+        """Makes the staged batch of the current slot available in `out` (dict of fp32 device tensors), then starts the copy of the
+        next batch into the other slot.  Stream-ordered: no host synchronisation."""
+        from . import ops
+        slot = self.slot
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self.ready[slot])
+        for k, v in self.slots[slot].items():
+            if k in self.classes:
+                ops.onehot_u8(v, self.classes[k], out=out[k])
+            else:
+                out[k].copy_(v, non_blocking=True)
+        self.free[slot].record(cur)
+        self.slot ^= 1
+        self.prefetch(self.slot)
+        return out
 
 
 class _GraphMixin:
@@ -96,12 +163,18 @@ class _GraphMixin:
         cur.wait_stream(side)
         torch.cuda.synchronize()
         self._graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self._graph):
+        import torch.distributed as dist
+        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        # with NCCL inside the graph the process group's watchdog thread keeps polling CUDA events: thread-local capture mode keeps
+        # those calls from invalidating the capture
+        with torch.cuda.graph(self._graph, capture_error_mode="thread_local" if multi else "global"):
             self._graph_out = self.step(self._static, *step_args)
         return self
 
-    def replay(self, batch=None):
-        if batch is not None:
+    def replay(self, batch=None, feeder=None):
+        if feeder is not None:
+            feeder.consume(self._static)  # staged on the copy stream while the previous replay ran
+        elif batch is not None:
             for k, v in batch.items():
                 self._static[k].copy_(v, non_blocking=True)
         self._graph.replay()
@@ -114,15 +187,17 @@ class Stage2Trainer(_GraphMixin):
     """Holds the optimisers / criteria of train_generator.py:145-159 and runs one step."""
 
     def __init__(self, tocg, generator, discriminator, vgg, lambda_feat=10.0, lambda_vgg=10.0, g_lr=1e-4, d_lr=4e-4,
-                 reducers=None):
+                 reducers=None, occlusion=True):
         from .spade import GANLoss
         self.tocg, self.G, self.D, self.vgg = tocg, generator, discriminator, vgg
         self.crit_gan = GANLoss("hinge")
         self.vgg_weights = [1.0 / 32, 1.0 / 16, 1.0 / 8, 1.0 / 4, 1.0]
         self.lambda_feat, self.lambda_vgg = lambda_feat, lambda_vgg
+        self.occlusion = occlusion  # opt.occlusion: the README trains stage 2 with --occlusion
         self.opt_g = torch.optim.Adam(generator.parameters(), lr=g_lr, betas=(0.0, 0.9), fused=True, capturable=True)
         self.opt_d = torch.optim.Adam(discriminator.parameters(), lr=d_lr, betas=(0.0, 0.9), fused=True, capturable=True)
         self.reducers = reducers or {}  # {"G": GradBucketReducer, "D": ...} for data-parallel runs
+        self._explicit_reduce = _attach_reducers(self.reducers)
 
     @staticmethod
     def _split(pred):
@@ -132,7 +207,7 @@ class Stage2Trainer(_GraphMixin):
 
     def step(self, batch, fine_h, fine_w):
         from . import autograd_g
-        g_in, parse = make_generator_inputs(self.tocg, batch, fine_h, fine_w)
+        g_in, parse = make_generator_inputs(self.tocg, batch, fine_h, fine_w, occlusion=self.occlusion)
         im = batch["image"]
         # ---------------- generator update (train_generator.py:279-322)
         out = self.G(g_in, parse)
@@ -148,8 +223,8 @@ class Stage2Trainer(_GraphMixin):
         loss_vgg = autograd_g.vgg_loss(self.vgg, self.vgg_weights, out, im) * self.lambda_vgg
         loss_gen = (loss_gan + loss_feat + loss_vgg).mean()
         self.opt_g.zero_grad(set_to_none=True)
-        loss_gen.backward()
-        if "G" in self.reducers:
+        loss_gen.backward()  # data-parallel: bucket all-reduces are launched from gradient hooks DURING this call (ddp.py)
+        if "G" in self.reducers and self._explicit_reduce:
             self.reducers["G"].reduce()
         self.opt_g.step()
         # ---------------- discriminator update (train_generator.py:327-360)
@@ -161,7 +236,7 @@ class Stage2Trainer(_GraphMixin):
         loss_dis = (self.crit_gan(pred_fake, False, for_discriminator=True) + self.crit_gan(pred_real, True, for_discriminator=True)).mean()
         self.opt_d.zero_grad(set_to_none=True)
         loss_dis.backward()
-        if "D" in self.reducers:
+        if "D" in self.reducers and self._explicit_reduce:
             self.reducers["D"].reduce()
         self.opt_d.step()
         return {"loss_gen": loss_gen.detach(), "loss_dis": loss_dis.detach(), "gan": loss_gan.detach(),
@@ -200,6 +275,7 @@ class Stage1Trainer(_GraphMixin):
         self.opt_g = torch.optim.Adam(tocg.parameters(), lr=lr, betas=(0.5, 0.999), fused=True, capturable=True)
         self.opt_d = torch.optim.Adam(D.parameters(), lr=lr, betas=(0.5, 0.999), fused=True, capturable=True)
         self.reducers = reducers or {}
+        self._explicit_reduce = _attach_reducers(self.reducers)
 
     @staticmethod
     def _remove_overlap(seg_out, warped_cm):  # train_condition.py:26-31
@@ -256,13 +332,13 @@ class Stage1Trainer(_GraphMixin):
         self.opt_d.zero_grad(set_to_none=True)
         loss_g.backward()
         d_stale = [p.grad for p in self.D.parameters()]  # the G loss also back-propagates into D: the reference zeroes it (optimizer_D.zero_grad)
-        if "G" in self.reducers:
+        if "G" in self.reducers and self._explicit_reduce:
             self.reducers["G"].reduce()
         self.opt_g.step()
         del d_stale
         self.opt_d.zero_grad(set_to_none=True)
         loss_d.backward()
-        if "D" in self.reducers:
+        if "D" in self.reducers and self._explicit_reduce:
             self.reducers["D"].reduce()
         self.opt_d.step()
         return {"loss_g": loss_g.detach(), "loss_d": loss_d.detach(), "l1": loss_l1.detach(), "vgg": loss_vgg.detach(), "ce": ce.detach()}

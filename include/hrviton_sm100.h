@@ -101,6 +101,14 @@ int hrv_instnorm_stats(const hrv_tensor* x0, int32_t x0_shift, const hrv_tensor*
                        const float* noise, const float* noise_scale, float eps,
                        float* mean, float* rstd, void* workspace, size_t workspace_bytes, hrv_stream stream);
 
+/* The same statistics for up to TWO norms that share the input but draw their own noise (norm_s and norm_0 of a SPADEResBlock,
+ * network_generator.py:160-170), from ONE pass over the SOURCE tensors: x0 is read at its own (half) resolution, the noise enters
+ * through the sums {sum nz, sum nz^2, sum x*nz} (see csrc/aux_kernels.cu).  noise1 / mean1 / rstd1 may be NULL (one norm).
+ * workspace: (4*N*C + 4*N) doubles. */
+int hrv_instnorm_stats2(const hrv_tensor* x0, int32_t x0_shift, const hrv_tensor* x1, int32_t h, int32_t w, const float* noise0,
+                        const float* noise_scale0, const float* noise1, const float* noise_scale1, float eps, float* mean0,
+                        float* rstd0, float* mean1, float* rstd1, void* workspace, size_t workspace_bytes, hrv_stream stream);
+
 /* y = act((x - mean[n,c]) * rstd[n,c]) elementwise on an NHWC bf16 tensor (InstanceNorm + LeakyReLU of the
  * discriminators, network_generator.py:269-270,427; networks.py:366-386). In place allowed. */
 int hrv_instnorm_apply(const hrv_tensor* x, const float* mean, const float* rstd, int32_t act,
@@ -201,9 +209,16 @@ int hrv_avgpool3s2_bwd(const hrv_tensor* dy, const hrv_tensor* dx, hrv_stream st
 /* train_generator.py:247-273 in one kernel: bilinear resize of the (n,c,h,w) fp32 class scores to (H,W) (align_corners=False),
  * 15x15 Gaussian blur (sigma 3, zero padding; tgm.image.GaussianBlur), arg-max over classes (first maximum).
  * idx (optional): (n,H,W) int64 class ids.  onehot (optional): (n,groups,H,W) fp32, channel group_of[class] set to 1
- * (group_of: HOST array of c entries; the 13 -> 7 label regrouping). */
+ * (group_of: HOST array of c entries; the 13 -> 7 label regrouping).  overlap (optional): (n,1,H,W) fp32 = sum over the classes
+ * whose bit is set in occl_mask of softmax_c(blurred scores) — the operand of remove_overlap under --occlusion
+ * (train_generator.py:26-31,242-243), computed with an online softmax so the 13 blurred planes never reach HBM. */
 int hrv_parse_blur_argmax(const float* seg, int32_t n, int32_t c, int32_t h, int32_t w, int32_t H, int32_t W,
-                          const int32_t* group_of, int32_t groups, int64_t* idx, float* onehot, hrv_stream stream);
+                          const int32_t* group_of, int32_t groups, int64_t* idx, float* onehot, uint32_t occl_mask,
+                          float* overlap, hrv_stream stream);
+
+/* Input feeding (cp_dataset.py:150-172 ships a one-hot fp32 parse map; here the host ships one byte per pixel):
+ * out (n,classes,h,w) fp32 with out[n,c,y,x] = (labels[n,y,x] == c). */
+int hrv_onehot_u8(const uint8_t* labels, int32_t n, int32_t classes, int32_t h, int32_t w, float* out, hrv_stream stream);
 
 /* tgm.image.GaussianBlur((ksize,ksize),(sigma,sigma)) on `planes` fp32 planes of h x w (train_generator.py:181,247;
  * test_generator.py:91,185): separable, zero padding ksize/2, taps exp(-d^2/(2 sigma^2)) normalised to sum 1; odd ksize <= 31. */
@@ -214,10 +229,14 @@ int hrv_gaussian_blur(const float* src, int32_t planes, int32_t h, int32_t w, in
  *   flow = F.interpolate(flow_lo (n,hl,wl,2), size=(h,w), bilinear, align_corners=False)      (any scale)
  *   g = flow / (div_x, div_y) + (lin_x[x], lin_y[y])          (correctly rounded fp32 division; lin_* = torch.linspace(-1,1,w|h))
  *   dst[n,:,y,x] = grid_sample(src (n,c,hs,ws) fp32 NCHW, g, bilinear, border, align_corners=False)
- * grid_out (optional): (n,h,w,2) fp32 receives g. */
+ * grid_out (optional): (n,h,w,2) fp32 receives g.
+ * mask_src (optional, (n,1,hs,ws)): the cloth mask, sampled with the same taps -> wm; overlap (optional, (n,1,h,w)):
+ * wm -= overlap*wm (remove_overlap); mask_out (optional) receives wm; composite != 0: dst = sample*wm + (1 - wm)
+ * (the white-background composite of train_generator.py:244 / test_generator.py:178). */
 int hrv_flow_warp_nchw(const float* flow_lo, int32_t n, int32_t hl, int32_t wl, const float* lin_x, const float* lin_y,
                        const float* src, int32_t c, int32_t hs, int32_t ws, float* dst, int32_t h, int32_t w, float div_x,
-                       float div_y, float* grid_out, hrv_stream stream);
+                       float div_y, float* grid_out, const float* mask_src, const float* overlap, float* mask_out,
+                       int32_t composite, hrv_stream stream);
 
 /* im2col for tiny-Cin convolutions: dst[n,y,x, (ky*kw+kx)*src.c + ci] = src[n, y+ky-pad, x+kx-pad, ci], zero outside the image
  * and in channels >= kh*kw*src.c.  Lets SPADE's 3x3 mlp_shared convolution over the 7-channel label map

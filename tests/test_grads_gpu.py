@@ -352,7 +352,7 @@ def test_stage2_losses_match_oracle_pipeline():
     # ---- product path (forward part of Stage2Trainer.step, generator update)
     bd = {k: v.cuda() for k, v in batch.items()}
     with torch.no_grad():
-        g_in, parse = train_step.make_generator_inputs(tocg, bd, h, w)
+        g_in, parse = train_step.make_generator_inputs(tocg, bd, h, w, occlusion=True)  # the README's --occlusion configuration
         out = G(g_in, parse)
         d_in = torch.cat((torch.cat((parse, out), 1), torch.cat((parse, bd["image"]), 1)), 0)
         pred = autograd_g.discriminator_forward_train(D, d_in, need_wgrad=False, as_float=True)
@@ -374,7 +374,7 @@ def test_stage2_losses_match_oracle_pipeline():
         return t
 
     with torch.no_grad():
-        g_in_r, parse_r = train_step.make_generator_inputs(_OracleTocg(), batch, h, w, unfused_parse=True)
+        g_in_r, parse_r = train_step.make_generator_inputs(_OracleTocg(), batch, h, w, unfused_parse=True, occlusion=True)
         out_r = orc.spade_generator_forward(sdg, g_in_r, parse_r, noise_cpu)
         pred_r = orc.gen_d_forward(sdd, torch.cat((torch.cat((parse_r, out_r), 1), torch.cat((parse_r, batch["image"]), 1)), 0))
         fake_r = [[t[:n] for t in p] for p in pred_r]
@@ -385,7 +385,9 @@ def test_stage2_losses_match_oracle_pipeline():
         vgg_cpu.load_state_dict(vgg_cpu_sd)
         fx, fy = vgg_cpu(out_r), vgg_cpu(batch["image"])
         vl_r = float(sum(wt * F.l1_loss(a, b) for wt, a, b in zip([1.0 / 32, 1.0 / 16, 1.0 / 8, 1.0 / 4, 1.0], fx, fy)))
-    print("STEP2LOSS parse agreement %.4f  image mean|d| %.3e" % (float((parse.cpu() == parse_r).float().mean()), float((out.cpu() - out_r).abs().mean())))
+    print("STEP2LOSS parse agreement %.4f  image mean|d| %.3e  warped-cloth (occlusion composite) max|d| %.3e" %
+          (float((parse.cpu() == parse_r).float().mean()), float((out.cpu() - out_r).abs().mean()), float((g_in.cpu()[:, 6:] - g_in_r[:, 6:]).abs().max())))
+    assert float((g_in.cpu()[:, 6:] - g_in_r[:, 6:]).abs().mean()) < 2e-3  # fused warp + remove_overlap + white composite vs the torch chain
     print("STEP2LOSS gan %.4f vs %.4f | feat %.4f vs %.4f | vgg %.4f vs %.4f" % (gan, gan_r, feat, feat_r, vl, vl_r))
     assert float((parse.cpu() == parse_r).float().mean()) > 0.99  # argmax of blurred logits: a few pixels may flip under bf16
     assert abs(gan - gan_r) < 0.05 + 0.05 * abs(gan_r)

@@ -464,3 +464,39 @@ def test_flow_warp_nchw_matches_torch_chain(shape):
     assert float((ggrid.cpu() - grid).abs().max()) < 2e-6
     # a sample coordinate within 2e-6 (normalised) of a pixel boundary may floor differently: compare values, which are continuous
     assert float((got.cpu() - want).abs().max()) < 2e-3 and float((got.cpu() - want).abs().mean()) < 1e-5
+
+
+@pytest.mark.parametrize("shift,c1,norms", [(1, 16, 2), (1, 16, 1), (0, 0, 2), (0, 8, 1), (1, 0, 2)])
+def test_instnorm_stats2_matches_fp64_statistics(shift, c1, norms):
+    """hrv_instnorm_stats2 (one pass over the SOURCE tensors, up to two norms with their own noise) against fp64 statistics of the
+    materialised virtual tensor cat(up2(x0), x1) + noise_j * ns_j (network_generator.py:101-113)."""
+    n, H, W, c0 = 2, 36, 20, 24
+    g = torch.Generator().manual_seed(3)
+    x0 = bf16r(torch.randn((n, c0, H >> shift, W >> shift), generator=g) * 2 + 0.5)
+    x1 = bf16r(torch.randn((n, c1, H, W), generator=g)) if c1 else None
+    full = F.interpolate(x0, scale_factor=2, mode="nearest") if shift else x0
+    if x1 is not None:
+        full = torch.cat([full, x1], 1)
+    C = c0 + c1
+    noises = [torch.randn((n, H, W), generator=g) for _ in range(norms)]
+    nss = [torch.randn(C, generator=g) * 0.3 for _ in range(norms)]
+    to_act = lambda t: Act(t.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).to(DEV))
+    outs = ops.instnorm_stats2(to_act(x0), shift, to_act(x1) if x1 is not None else None, H, W, [z.to(DEV) for z in noises],
+                               [s.to(DEV) for s in nss])
+    for j in range(norms):
+        v = (full + noises[j][:, None] * nss[j][None, :, None, None]).double()
+        m = v.mean((2, 3))
+        r = 1.0 / torch.sqrt(v.var((2, 3), unbiased=False) + 1e-5)
+        assert float((outs[j][0].cpu().double() - m).abs().max()) < 2e-5
+        assert float(((outs[j][1].cpu().double() - r) / r).abs().max()) < 2e-5
+    # without noise it reproduces the plain InstanceNorm statistics of the first kernel
+    plain = ops.instnorm_stats2(to_act(x0), shift, to_act(x1) if x1 is not None else None, H, W, [None], [None])[0]
+    ref = ops.instnorm_stats(to_act(x0), shift, to_act(x1) if x1 is not None else None, H, W, None, None)
+    assert float((plain[0] - ref[0]).abs().max()) < 1e-5 and float(((plain[1] - ref[1]) / ref[1]).abs().max()) < 1e-5
+
+
+def test_onehot_u8():
+    lab = torch.randint(0, 13, (3, 1, 37, 29), dtype=torch.uint8)
+    got = ops.onehot_u8(lab.to(DEV), 13).cpu()
+    want = torch.zeros(3, 13, 37, 29).scatter_(1, lab.long(), 1.0)
+    assert torch.equal(got, want)

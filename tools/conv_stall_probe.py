@@ -1,0 +1,68 @@
+"""Where does the classic tcgen05 convolution kernel lose time?  Runs representative layers with the kernel's per-CTA stall counters
+switched on (hrv_debug_set_conv_stats) and prints, per layer, the share of the MMA warp's life spent waiting for the A ring, the B
+(weight) ring and a free TMEM accumulator, the producer warp's waits for free stages, and the first epilogue warp's wait for
+accumulators.  Usage: python tools/conv_stall_probe.py [batch]   (env HRV_CONV_HALO etc. select kernel variants)"""
+import ctypes
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import hrv_loader  # noqa: E402
+
+hrv_loader.load()
+from hrviton_b200 import capi, ops  # noqa: E402
+from hrviton_b200.ops import Act  # noqa: E402
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 4
+L = capi.lib()
+L.hrv_debug_set_conv_stats.argtypes = [ctypes.c_void_p]
+L.hrv_debug_set_conv_stats.restype = None
+stats = torch.zeros(148 * 16, dtype=torch.int64, device="cuda")
+cases = [  # cin, n_gemm, k, h, w, spade
+    (128, 160, 3, 1024, 768, True), (128, 288, 3, 512, 384, True), (128, 544, 3, 256, 192, True), (128, 64, 3, 1024, 768, True),
+    (160, 160, 3, 1024, 768, False), (256, 256, 3, 256, 192, False), (512, 512, 3, 128, 96, False), (1040, 512, 3, 64, 48, False),
+    (80, 160, 3, 1024, 768, False)]
+os.environ["HRV_CONV_PIXN"] = "0"
+print("%-34s %8s %8s | MMA warp: %6s %6s %6s %6s | producer: %6s %6s | epilogue w4: %6s" %
+      ("layer", "ms", "TFLOP/s", "issue", "waitA", "waitB", "waitD", "freeA", "freeB", "waitAcc"))
+for cin, ng, k, h, w, spade in cases:
+    x = Act(torch.randn(B, h, w, ops.round_up(cin, 8), device="cuda").to(torch.bfloat16), c=cin)
+    if spade:
+        C = ng // 2
+        wt = torch.randn(C, cin, k, k, device="cuda") * 0.05
+        pw = ops.pack_weight(wt, (k // 2, k // 2), interleave=wt.clone())
+        x0 = Act(torch.randn(B, h, w, C, device="cuda").to(torch.bfloat16))
+        mean = torch.zeros(B, C, device="cuda"); rstd = torch.ones(B, C, device="cuda")
+        noise = torch.randn(B, h, w, device="cuda"); ns = torch.zeros(C, device="cuda"); sh = torch.zeros(2 * C, device="cuda")
+        out = Act.empty(B, h, w, C)
+        fn = lambda: ops.conv2d_spade(x, pw, out, x0, 0, None, mean, rstd, noise, ns, sh, 2)
+    else:
+        wt = torch.randn(ng, cin, k, k, device="cuda") * 0.05
+        pw = ops.pack_weight(wt, (k // 2, k // 2))
+        out = Act.empty(B, h, w, ng)
+        fn = lambda: ops.conv2d(x, pw, out)
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    stats.zero_()
+    L.hrv_debug_set_conv_stats(ctypes.c_void_p(stats.data_ptr()))
+    fn()
+    torch.cuda.synchronize()
+    L.hrv_debug_set_conv_stats(None)
+    s = stats.view(148, 16).double()
+    s = s[s[:, 0] > 0]
+    tot = s[:, 0].mean()
+    f = lambda i: float(s[:, i].mean() / tot)
+    fl = 2.0 * cin * ng * k * k * B * h * w
+    print("%4d->%4d k%d %4dx%-4d %-7s %8.3f %8.1f |           %5.1f%% %5.1f%% %5.1f%% %5.1f%% |           %5.1f%% %5.1f%% |              %5.1f%%   (%d CTAs, %.0f tiles/CTA, %.0f cyc/tile)"
+          % (cin, ng, k, h, w, "spade" if spade else "linear", ms, fl / ms / 1e9, 100 * (1 - f(1) - f(2) - f(3)), 100 * f(1), 100 * f(2), 100 * f(3),
+             100 * f(4), 100 * f(5), 100 * float(s[:, 6].mean() / s[:, 7].mean()), s.shape[0], float(s[:, 8].mean()), float(tot / s[:, 8].mean())), flush=True)
