@@ -52,7 +52,10 @@ class ConvFn(torch.autograd.Function):
     need_wgrad=False skips dW (frozen nets: VGG, D inside the G step)."""
 
     @staticmethod
-    def forward(ctx, x_buf, w, bias, res_buf, act, out_fp32_nchw, pad, out_f32_nhwc, out_hw=None):
+    def forward(ctx, x_buf, w, bias, res_buf, act, out_fp32_nchw, pad, out_f32_nhwc, out_hw=None, gate_in=ACT_NONE, gated_out=False):
+        """gate_in: x_buf is the saved OUTPUT of a layer with that activation whose backward this node's data-gradient convolution
+        applies in its epilogue (dx *= act'(x_buf)).  gated_out: every consumer of y applies this node's activation backward itself, so
+        backward() receives dL/dv directly.  Together they remove the dv = dy * act'(y) pass from ReLU chains (Vgg19)."""
         cout, cin, kh, kw = w.shape
         n, h, wd, _ = x_buf.shape
         oh, ow = h + 2 * pad - kh + 1, wd + 2 * pad - kw + 1
@@ -74,8 +77,9 @@ class ConvFn(torch.autograd.Function):
             ya = Act.empty(n, oh, ow, cout)
             ops.conv2d(xa, pw, ya, act=act, shift=b, res=res)
             y = ya.buf
-        ctx.save_for_backward(x_buf, w, y if act != ACT_NONE else None)
-        ctx.meta = (act, out_fp32_nchw, bias is not None, res_buf is not None, pad, out_f32_nhwc)
+        ctx.save_for_backward(x_buf, w, y if (act != ACT_NONE and not gated_out) else None)
+        ctx.meta = (act if not gated_out else ACT_NONE, out_fp32_nchw, bias is not None, res_buf is not None, pad, out_f32_nhwc)
+        ctx.gate_in = gate_in
         return y
 
     @staticmethod
@@ -104,18 +108,23 @@ class ConvFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             pw = ops.pack_weight(w, (kh - 1 - pad, kw - 1 - pad), dgrad=True)  # flipped/transposed operand, packed in one kernel
             dxa = Act.empty(n, h, wd, cin, pitch=x_buf.shape[3], zero=x_buf.shape[3] > ops.round_up(cin, 8))
-            ops.conv2d(Act(dv_buf, c=cout), pw, dxa)
+            if ctx.gate_in != ACT_NONE:  # activation backward of the producer of x_buf, fused into this convolution's epilogue
+                mode = {ACT_RELU: ops.capi.RES_GATE_RELU, ACT_LRELU: ops.capi.RES_GATE_LRELU}[ctx.gate_in]
+                ops.conv2d(Act(dv_buf, c=cout), pw, dxa, res=Act(x_buf, c=cin), res_mode=mode)
+            else:
+                ops.conv2d(Act(dv_buf, c=cout), pw, dxa)
             dx = dxa.buf
         if ctx.needs_input_grad[1]:
             dw = _wgrad(x_buf, cin, dv_buf, cout, kh, kw, pad)
         if has_res and ctx.needs_input_grad[3]:
             dres = dv_buf
-        return dx, dw, db, dres, None, None, None, None, None
+        return dx, dw, db, dres, None, None, None, None, None, None, None
 
 
-def conv(x_buf, w, bias=None, res_buf=None, act=ACT_NONE, out_fp32_nchw=False, pad=None, out_f32_nhwc=False, out_hw=None):
+def conv(x_buf, w, bias=None, res_buf=None, act=ACT_NONE, out_fp32_nchw=False, pad=None, out_f32_nhwc=False, out_hw=None, gate_in=ACT_NONE,
+         gated_out=False):
     pad = w.shape[2] // 2 if pad is None else pad
-    return ConvFn.apply(x_buf, w, bias, res_buf, act, out_fp32_nchw, pad, out_f32_nhwc, out_hw)
+    return ConvFn.apply(x_buf, w, bias, res_buf, act, out_fp32_nchw, pad, out_f32_nhwc, out_hw, gate_in, gated_out)
 
 
 class SpadeFn(torch.autograd.Function):
@@ -269,14 +278,15 @@ class MaxPool2Fn(torch.autograd.Function):
     """nn.MaxPool2d(2,2) on a pixel-major bf16 buffer (Vgg19, networks.py:201-231): hrv_maxpool2_fwd / hrv_maxpool2_bwd."""
 
     @staticmethod
-    def forward(ctx, x_buf):
+    def forward(ctx, x_buf, relu_gate=False):
         ctx.save_for_backward(x_buf)
+        ctx.relu_gate = relu_gate  # x_buf is a ReLU output whose producer expects dL/dv: apply (x > 0) while routing
         return ops.maxpool2(Act(x_buf)).buf
 
     @staticmethod
     def backward(ctx, dy):
         (x_buf,) = ctx.saved_tensors
-        return ops.maxpool2_bwd(Act(x_buf), Act(dy.contiguous())).buf
+        return ops.maxpool2_bwd(Act(x_buf), Act(dy.contiguous()), relu_gate=ctx.relu_gate).buf, None
 
 
 class AvgPool3S2Fn(torch.autograd.Function):
@@ -387,12 +397,17 @@ def vgg_features(vgg, x_nchw):
     Returns the 5 slice outputs as pixel-major bf16 buffers."""
     h = FromNCHW.apply(x_nchw, None, None)
     outs = []
+    relu_out = False  # is h the output of a conv+ReLU whose backward its consumers apply (gated_out)?
     for k in range(5):
         for layer in getattr(vgg, "slice%d" % (k + 1)):
             if isinstance(layer, torch.nn.Conv2d):
-                h = conv(h, layer.weight, layer.bias, act=ACT_RELU)
+                # ReLU backward is never a pass of its own: the consumer of each activation (next convolution's data gradient,
+                # max-pool backward, L1 backward) multiplies by (y > 0) in its epilogue
+                h = conv(h, layer.weight, layer.bias, act=ACT_RELU, gate_in=ACT_RELU if relu_out else ACT_NONE, gated_out=True)
+                relu_out = True
             elif isinstance(layer, torch.nn.MaxPool2d):
-                h = MaxPool2Fn.apply(h)
+                h = MaxPool2Fn.apply(h, relu_out)
+                relu_out = False
             elif isinstance(layer, torch.nn.ReLU):
                 pass  # fused into the preceding convolution's epilogue
             else:
@@ -405,15 +420,16 @@ class L1MeanFn(torch.autograd.Function):
     """mean |a - b| over two pixel-major bf16 buffers (b carries no gradient): hrv_l1_sum / hrv_l1_bwd, one pass each."""
 
     @staticmethod
-    def forward(ctx, a_buf, b_buf):
+    def forward(ctx, a_buf, b_buf, relu_gate=False):
         ctx.save_for_backward(a_buf, b_buf)
+        ctx.relu_gate = relu_gate  # a_buf is a ReLU output whose producer expects dL/dv
         return (ops.l1_sum(Act(a_buf), Act(b_buf)) / a_buf.numel()).float().reshape(())
 
     @staticmethod
     def backward(ctx, g):
         a_buf, b_buf = ctx.saved_tensors
         gscale = (g.float() / a_buf.numel()).reshape(1).contiguous()
-        return ops.l1_bwd(Act(a_buf), Act(b_buf), gscale).buf, None
+        return ops.l1_bwd(Act(a_buf), Act(b_buf), gscale, relu_gate=ctx.relu_gate).buf, None, None
 
 
 def vgg_loss(vgg, weights, x, y):
@@ -423,5 +439,5 @@ def vgg_loss(vgg, weights, x, y):
     fx = vgg_features(vgg, x)
     loss = 0
     for wgt, tx, ty in zip(weights, fx, fy):
-        loss = loss + wgt * L1MeanFn.apply(tx, ty)
+        loss = loss + wgt * L1MeanFn.apply(tx, ty, True)  # every slice output is a conv+ReLU output with gated_out=True
     return loss

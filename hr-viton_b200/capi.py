@@ -10,8 +10,9 @@ BF16, F32 = 0, 1  # hrv_dtype codes: 0 = the flavour's 16-bit storage type (bf16
 ACT_NONE, ACT_RELU, ACT_LRELU, ACT_TANH = 0, 1, 2, 3
 NHWC, NCHW = 0, 1
 EPI_LINEAR, EPI_SPADE = 0, 1
+RES_ADD, RES_GATE_RELU, RES_GATE_LRELU = 0, 1, 2
 
-EXPORTS = ["hrv_conv2d_fwd", "hrv_instnorm_stats", "hrv_instnorm_stats2", "hrv_instnorm_apply", "hrv_norm_apply_affine", "hrv_norm_bwd_reduce", "hrv_norm_bwd_apply", "hrv_act_bwd_bias", "hrv_conv2d_wgrad", "hrv_nchw_to_nhwc", "hrv_nhwc_to_nchw",
+EXPORTS = ["hrv_conv2d_fwd", "hrv_instnorm_stats", "hrv_instnorm_stats2", "hrv_instnorm_apply", "hrv_norm_apply_affine", "hrv_norm_bwd_reduce", "hrv_norm_bwd_apply", "hrv_act_bwd_bias", "hrv_conv2d_wgrad", "hrv_conv2d_wgrad_workspace_bytes", "hrv_nchw_to_nhwc", "hrv_nhwc_to_nchw",
            "hrv_space_to_depth", "hrv_avgpool3s2", "hrv_bilinear_up2_add", "hrv_flow_warp", "hrv_bilinear_up2_bwd", "hrv_flow_warp_bwd", "hrv_pack_conv_weight", "hrv_space_to_depth_bwd", "hrv_maxpool2_fwd", "hrv_maxpool2_bwd",
            "hrv_avgpool3s2_bwd", "hrv_parse_blur_argmax", "hrv_gaussian_blur", "hrv_flow_warp_nchw", "hrv_onehot_u8", "hrv_im2col", "hrv_l1_sum", "hrv_l1_bwd", "hrv_last_error",
            "hrv_version", "hrv_device_sm_count"]
@@ -30,7 +31,7 @@ class ConvParams(ctypes.Structure):
                 ("scale", ctypes.c_void_p), ("shift", ctypes.c_void_p),
                 ("res", Tensor), ("x0", Tensor), ("x1", Tensor), ("x0_shift", ctypes.c_int32),
                 ("mean", ctypes.c_void_p), ("rstd", ctypes.c_void_p), ("noise", ctypes.c_void_p),
-                ("noise_scale", ctypes.c_void_p), ("gamma_out", Tensor)]
+                ("noise_scale", ctypes.c_void_p), ("gamma_out", Tensor), ("res_mode", ctypes.c_int32)]
 
 
 FLAVOURED = [n for n in EXPORTS if n not in ("hrv_last_error", "hrv_version", "hrv_device_sm_count")]
@@ -73,7 +74,8 @@ def lib(dtype=None):
     L.hrv_norm_apply_affine.argtypes = [TP, vp, vp, vp, vp, TP, i32, TP, vp]
     L.hrv_norm_bwd_apply.argtypes = [TP, TP, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, TP, vp, vp]
     L.hrv_act_bwd_bias.argtypes = [TP, TP, i32, TP, vp, vp]
-    L.hrv_conv2d_wgrad.argtypes = [TP, TP, i32, i32, i32, vp, vp]
+    L.hrv_conv2d_wgrad.argtypes = [TP, TP, i32, i32, i32, vp, vp, ctypes.c_size_t, vp]
+    L.hrv_conv2d_wgrad_workspace_bytes.argtypes = [TP, TP, i32, i32]
     L.hrv_nchw_to_nhwc.argtypes = [vp, i32, i32, i32, TP, vp]
     L.hrv_nhwc_to_nchw.argtypes = [TP, vp, vp]
     L.hrv_space_to_depth.argtypes = [TP, TP, vp]
@@ -83,7 +85,7 @@ def lib(dtype=None):
     L.hrv_bilinear_up2_bwd.argtypes = [TP, TP, vp]
     L.hrv_space_to_depth_bwd.argtypes = [TP, TP, vp]
     L.hrv_maxpool2_fwd.argtypes = [TP, TP, vp]
-    L.hrv_maxpool2_bwd.argtypes = [TP, TP, TP, vp]
+    L.hrv_maxpool2_bwd.argtypes = [TP, TP, TP, i32, vp]
     L.hrv_avgpool3s2_bwd.argtypes = [TP, TP, vp]
     L.hrv_parse_blur_argmax.argtypes = [vp, i32, i32, i32, i32, i32, i32, ctypes.POINTER(ctypes.c_int32), i32, vp, vp, ctypes.c_uint32, vp, vp]
     L.hrv_onehot_u8.argtypes = [vp, i32, i32, i32, i32, vp, vp]
@@ -91,7 +93,7 @@ def lib(dtype=None):
     L.hrv_flow_warp_nchw.argtypes = [vp, i32, i32, i32, vp, vp, vp, i32, i32, i32, vp, i32, i32, f32, f32, vp, vp, vp, vp, i32, vp]
     L.hrv_im2col.argtypes = [TP, TP, i32, i32, i32, vp]
     L.hrv_l1_sum.argtypes = [TP, TP, vp, vp]
-    L.hrv_l1_bwd.argtypes = [TP, TP, vp, TP, vp]
+    L.hrv_l1_bwd.argtypes = [TP, TP, vp, TP, i32, vp]
     L.hrv_pack_conv_weight.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp, vp, i32, i32, vp]
     L.hrv_flow_warp_bwd.argtypes = [vp, vp, vp, TP, TP, vp, vp, vp, vp]
     for name in FLAVOURED:
@@ -99,7 +101,9 @@ def lib(dtype=None):
         twin.argtypes = getattr(L, name).argtypes
     for name in EXPORTS + EXPORTS_F16:
         fn = getattr(L, name)
-        if name != "hrv_last_error":
+        if name.startswith("hrv_conv2d_wgrad_workspace_bytes"):
+            fn.restype = ctypes.c_size_t
+        elif name != "hrv_last_error":
             fn.restype = ctypes.c_int
     _lib = L
     return L

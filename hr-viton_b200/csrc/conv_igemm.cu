@@ -38,13 +38,6 @@ constexpr int kThreadsC = 128 + 128 * kEpiC;
 struct alignas(64) ConvArgs {
   CUtensorMap tmA;
   CUtensorMap tmB;
-  CUtensorMap tmOut;  // staged epilogue: bf16 NHWC output {store_c, W, H, N}, box {64|32 channels, TW, TH, TN}
-  CUtensorMap tmGam;  // staged epilogue: gamma_out of the SPADE training forward
-  CUtensorMap tmOutT, tmGamT;  // the same for the LAST slab of an N tile whose width is not a multiple of 64 columns: box = the remaining
-                               // channels only (dense rows, no swizzle) so that the store never reaches into the next N tile's channels
-  int tail_cols;               // BN % 64 (0: every slab is full)
-  int stage_out;      // 1 = epilogue writes through shared memory + TMA stores (bf16 NHWC outputs); 0 = per-thread global stores
-  uint32_t epi_off;   // byte offset (from the 1 KB aligned base) of the kEpiC staging buffers, epi_wg_bytes each
   int Nimg, Hout, Wout;
   int tw_log, th_log;
   int tiles_x, tiles_y, tiles_img, tiles_n;
@@ -57,7 +50,7 @@ struct alignas(64) ConvArgs {
   void* out;
   int out_pitch, out_dtype, out_layout, out_c;
   const void* res;
-  int res_pitch, res_dtype;
+  int res_pitch, res_dtype, res_mode;  // res_mode: 0 add, 1 ReLU gate, 2 LeakyReLU(0.2) gate (bf16 res only)
   const __nv_bfloat16* x0;
   int x0_c, x0_pitch, x0_shift;
   const __nv_bfloat16* x1;
@@ -70,7 +63,6 @@ struct alignas(64) ConvArgs {
   __nv_bfloat16* gamma_out;
   int gamma_pitch;
   int pairs, tiles_m, store_c;  // pixel-N variant: 256-pixel tiles (pairs of 128-pixel boxes), channels written per pixel
-  uint32_t epi_wg_bytes, epi_buf_bytes;
   unsigned long long* stats;    // debug (tools/conv_stall_probe.py): per-CTA cycle counters of the warp roles, or nullptr
 };
 
@@ -106,7 +98,7 @@ __global__ void __launch_bounds__(kThreadsC, 1) conv_igemm_kernel(const __grid_c
   const uint32_t NACC = (uint32_t)a.nacc;
   const uint32_t b_bytes = (uint32_t)a.BN * ROW_BYTES;
   const uint32_t stage_bytes = a.halo ? (uint32_t)a.a_stage_bytes : A_BYTES + ((b_bytes + 1023u) & ~1023u);
-  const uint32_t stage0 = base + 2048u + (a.stage_out ? (uint32_t)kEpiC * a.epi_wg_bytes : 0u);  // epilogue staging tiles sit before the rings
+  const uint32_t stage0 = base + 2048u;
   const uint32_t bstage0 = stage0 + (uint32_t)a.stages * stage_bytes;  // halo mode: weight ring after the halo ring
 
   const int warp = threadIdx.x >> 5;
@@ -121,14 +113,6 @@ __global__ void __launch_bounds__(kThreadsC, 1) conv_igemm_kernel(const __grid_c
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&a.tmA);
     tma_prefetch_desc(&a.tmB);
-    if (a.stage_out) {
-      tma_prefetch_desc(&a.tmOut);
-      if (a.gamma_out) tma_prefetch_desc(&a.tmGam);
-      if (a.tail_cols) {
-        tma_prefetch_desc(&a.tmOutT);
-        if (a.gamma_out) tma_prefetch_desc(&a.tmGamT);
-      }
-    }
   } else if (warp == 1 && lane == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(bar_full(s), 1);
@@ -332,8 +316,8 @@ __global__ void __launch_bounds__(kThreadsC, 1) conv_igemm_kernel(const __grid_c
     const int wg = (warp - 4) >> 2;     // epilogue warpgroup: owns 16-column chunks wg, wg+kEpiC, ...
     const int r = q * 32 + lane;
     const int tw_mask = (1 << a.tw_log) - 1, th_mask = (1 << a.th_log) - 1;
-    uint32_t acc = 0, aph = 0, tile_it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_it) {
+    uint32_t acc = 0, aph = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int nt = tile % a.tiles_n;
       int mt = tile / a.tiles_n;
       const int tx = mt % a.tiles_x;
@@ -349,174 +333,7 @@ __global__ void __launch_bounds__(kThreadsC, 1) conv_igemm_kernel(const __grid_c
       const int n_base = nt * a.BN;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)a.BN;
 
-      if (a.stage_out) {
-        // ================= staged epilogue (bf16 NHWC outputs): the tile's output leaves through shared memory and TMA stores.
-        // Per-thread global stores write 16 bytes at the pixel pitch — 32 different lines per warp instruction — and that LSU
-        // traffic, not the tensor pipe, bounded every wide-N convolution (tools/conv_stall_probe.py, profiles/r2_conv_stall*.txt).
-        // Work unit = one SLAB of 64 GEMM columns (LINEAR: 64 channels = 128-byte rows, SWIZZLE_128B; SPADE: 32 channels of
-        // (gamma,beta) pairs = 64-byte rows, SWIZZLE_64B); slab s of tile number t belongs to warpgroup (s + t) mod kEpiC, which
-        // converts it into its private staging tile [128 pixels][row] and has one thread issue the TMA store (the tensor map clips
-        // pixels / channels outside the tensor).
-        const bool spade = a.epi != 0;
-        const uint32_t so = base + a.epi_off + (uint32_t)wg * a.epi_wg_bytes;  // staging tile of the output
-        const uint32_t sg = so + a.epi_buf_bytes;                                // ... and of gamma_out (SPADE training forward)
-        const int n_slabs = (a.BN + 63) >> 6;
-        const int tile_x0 = tx << a.tw_log, tile_y0 = ty << a.th_log, tile_n0 = ti << (7 - a.tw_log - a.th_log);
-        const int sh0 = a.x0_shift;
-        const long long pix0 = spade ? ((long long)n * (a.Hout >> sh0) + (y >> sh0)) * (a.Wout >> sh0) + (x >> sh0) : 0;
-        const float nz = (spade && valid && a.noise) ? __ldg(a.noise + pix) : 0.f;
-        bool waited = false;
-        for (int sl = (wg + kEpiC - (int)(tile_it % kEpiC)) % kEpiC; sl < n_slabs; sl += kEpiC) {
-          const int colb = sl * 64;
-          const bool tail = a.tail_cols != 0 && sl == n_slabs - 1;  // narrower last slab: dense rows of tail_cols (LINEAR) / tail_cols/2 (SPADE) channels
-          const uint32_t trow = (uint32_t)a.tail_cols * (spade ? 1u : 2u);  // its row pitch in bytes
-          // ---- operands that do not depend on the accumulator go first: x (SPADE) / residual (LINEAR) of the slab's 4 chunks
-          uint4 pre[4][2];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            pre[k][0] = make_uint4(0, 0, 0, 0);
-            pre[k][1] = make_uint4(0, 0, 0, 0);
-            const int col = colb + k * 16;
-            if (col >= a.BN || !valid) continue;
-            if (spade) {
-              const int c0 = (n_base + col) >> 1;
-              if (c0 < a.C_mod) {
-                const __nv_bfloat16* xp = (c0 < a.x0_c) ? (a.x0 + pix0 * a.x0_pitch + c0) : (a.x1 + pix * a.x1_pitch + (c0 - a.x0_c));
-                pre[k][0] = __ldg(reinterpret_cast<const uint4*>(xp));
-              }
-            } else if (a.res && a.res_dtype == 0) {
-              const int j0 = n_base + col;
-              const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(a.res) + pix * a.res_pitch + j0;
-              if (j0 < a.out_c) pre[k][0] = __ldg(reinterpret_cast<const uint4*>(rp));
-              if (j0 + 8 < a.out_c) pre[k][1] = __ldg(reinterpret_cast<const uint4*>(rp) + 1);
-            }
-          }
-          if (!waited) {
-            mbar_wait_acct(bar_tfull(acc), aph, acct, w0);
-            tc_fence_after();
-            waited = true;
-          }
-          // ---- the previous TMA store of this warpgroup must have finished reading the staging tile
-          if (r == 0) bulk_wait_read<0>();
-          named_bar_sync(1 + wg, 128);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int col = colb + k * 16;
-            if (col >= a.BN) break;
-            uint32_t v[16];
-            __syncwarp();
-            tmem_ld16(taddr + col, v);
-            tmem_wait_ld();
-            if (spade) {
-              const int c0 = (n_base + col) >> 1;
-              float o[8], gmv[8];
-              if (c0 < a.C_mod) {
-                float mu[8], rs[8], nsv[8], sh[16];
-                const float4* mp = reinterpret_cast<const float4*>(a.mean + (long long)(valid ? n : 0) * a.C_mod + c0);
-                const float4* rp = reinterpret_cast<const float4*>(a.rstd + (long long)(valid ? n : 0) * a.C_mod + c0);
-                *reinterpret_cast<float4*>(mu) = __ldg(mp);
-                *reinterpret_cast<float4*>(mu + 4) = __ldg(mp + 1);
-                *reinterpret_cast<float4*>(rs) = __ldg(rp);
-                *reinterpret_cast<float4*>(rs + 4) = __ldg(rp + 1);
-                if (a.noise_scale) {
-                  const float4* np_ = reinterpret_cast<const float4*>(a.noise_scale + c0);
-                  *reinterpret_cast<float4*>(nsv) = __ldg(np_);
-                  *reinterpret_cast<float4*>(nsv + 4) = __ldg(np_ + 1);
-                } else {
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) nsv[i] = 0.f;
-                }
-                if (a.shift) {
-                  const float4* sp = reinterpret_cast<const float4*>(a.shift + 2 * c0);
-#pragma unroll
-                  for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(sh + 4 * i) = __ldg(sp + i);
-                } else {
-#pragma unroll
-                  for (int i = 0; i < 16; ++i) sh[i] = 0.f;
-                }
-                const uint4 xk = pre[k][0];
-                const float xs[8] = {bf16_lo(xk.x), bf16_hi(xk.x), bf16_lo(xk.y), bf16_hi(xk.y),
-                                     bf16_lo(xk.z), bf16_hi(xk.z), bf16_lo(xk.w), bf16_hi(xk.w)};
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  const float xval = fmaf(nz, nsv[i], xs[i]);
-                  const float gm = __uint_as_float(v[2 * i]) + sh[2 * i];
-                  const float bt = __uint_as_float(v[2 * i + 1]) + sh[2 * i + 1];
-                  const float xn = (xval - mu[i]) * rs[i];
-                  gmv[i] = gm;
-                  o[i] = apply_act(fmaf(xn, 1.f + gm, bt), a.act);
-                }
-              } else {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) { o[i] = 0.f; gmv[i] = 0.f; }
-              }
-              // 64-byte rows, SWIZZLE_64B: 16-byte piece k of row r lives at piece k ^ ((r >> 1) & 3); the tail slab is dense
-              const uint32_t off = tail ? (uint32_t)r * trow + (uint32_t)(k << 4) : (uint32_t)r * 64u + (uint32_t)((k ^ ((r >> 1) & 3)) << 4);
-              st_shared_v4(so + off, make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7])));
-              if (a.gamma_out)
-                st_shared_v4(sg + off, make_uint4(pack_bf16(gmv[0], gmv[1]), pack_bf16(gmv[2], gmv[3]), pack_bf16(gmv[4], gmv[5]), pack_bf16(gmv[6], gmv[7])));
-            } else {
-#pragma unroll
-              for (int g = 0; g < 2; ++g) {
-                const int jg = n_base + col + g * 8;
-                float f[8];
-                if (jg + 8 <= a.n_gemm) {  // vector path (scale/shift arrays are 16-byte aligned torch allocations)
-                  float sc[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f}, sh[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                  if (a.scale) {
-                    *reinterpret_cast<float4*>(sc) = __ldg(reinterpret_cast<const float4*>(a.scale + jg));
-                    *reinterpret_cast<float4*>(sc + 4) = __ldg(reinterpret_cast<const float4*>(a.scale + jg) + 1);
-                  }
-                  if (a.shift) {
-                    *reinterpret_cast<float4*>(sh) = __ldg(reinterpret_cast<const float4*>(a.shift + jg));
-                    *reinterpret_cast<float4*>(sh + 4) = __ldg(reinterpret_cast<const float4*>(a.shift + jg) + 1);
-                  }
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) f[i] = fmaf(__uint_as_float(v[g * 8 + i]), sc[i], sh[i]);
-                } else {
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) {
-                    const int j = jg + i;
-                    const bool in = j < a.n_gemm;
-                    const float sc = in ? (a.scale ? __ldg(a.scale + j) : 1.f) : 0.f;
-                    const float sh = (in && a.shift) ? __ldg(a.shift + j) : 0.f;
-                    f[i] = fmaf(__uint_as_float(v[g * 8 + i]), sc, sh);
-                  }
-                }
-                if (a.res) {
-                  if (a.res_dtype == 0) {
-                    const uint4 rv = pre[k][g];
-                    f[0] += bf16_lo(rv.x); f[1] += bf16_hi(rv.x); f[2] += bf16_lo(rv.y); f[3] += bf16_hi(rv.y);
-                    f[4] += bf16_lo(rv.z); f[5] += bf16_hi(rv.z); f[6] += bf16_lo(rv.w); f[7] += bf16_hi(rv.w);
-                  } else if (valid) {
-                    const float* rp = reinterpret_cast<const float*>(a.res) + pix * a.res_pitch + jg;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                      if (jg + i < a.out_c) f[i] += __ldg(rp + i);
-                  }
-                }
-#pragma unroll
-                for (int i = 0; i < 8; ++i) f[i] = apply_act(f[i], a.act);
-                // 128-byte rows, SWIZZLE_128B: 16-byte piece p of row r lives at piece p ^ (r & 7); the tail slab is dense
-                const int pc = 2 * k + g;
-                st_shared_v4(so + (tail ? (uint32_t)r * trow + (uint32_t)(pc << 4) : (uint32_t)r * 128u + (uint32_t)((pc ^ (r & 7)) << 4)),
-                             make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7])));
-              }
-            }
-          }
-          fence_proxy_async();          // generic-proxy writes of the staging tile -> visible to the TMA (async proxy)
-          named_bar_sync(1 + wg, 128);  // staging tile complete
-          if (r == 0) {
-            const int cb = spade ? ((n_base + colb) >> 1) : (n_base + colb);
-            tma_store_4d(tail ? &a.tmOutT : &a.tmOut, so, cb, tile_x0, tile_y0, tile_n0);
-            if (spade && a.gamma_out) tma_store_4d(tail ? &a.tmGamT : &a.tmGam, sg, cb, tile_x0, tile_y0, tile_n0);
-            bulk_commit();
-          }
-        }
-        if (!waited) {  // no slab of this tile was ours: stay in step with the accumulator ring before releasing it
-          mbar_wait_acct(bar_tfull(acc), aph, acct, w0);
-          tc_fence_after();
-        }
-      } else if (a.epi == 0) {
+      if (a.epi == 0) {
         mbar_wait_acct(bar_tfull(acc), aph, acct, w0);
         tc_fence_after();
         // ---------------- LINEAR
@@ -559,8 +376,15 @@ __global__ void __launch_bounds__(kThreadsC, 1) conv_igemm_kernel(const __grid_c
               if (a.res_dtype == 0) {
                 const uint4 rv = __ldg(reinterpret_cast<const uint4*>(
                     reinterpret_cast<const __nv_bfloat16*>(a.res) + pix * a.res_pitch + jg));
-                f[0] += bf16_lo(rv.x); f[1] += bf16_hi(rv.x); f[2] += bf16_lo(rv.y); f[3] += bf16_hi(rv.y);
-                f[4] += bf16_lo(rv.z); f[5] += bf16_hi(rv.z); f[6] += bf16_lo(rv.w); f[7] += bf16_hi(rv.w);
+                const float rf[8] = {bf16_lo(rv.x), bf16_hi(rv.x), bf16_lo(rv.y), bf16_hi(rv.y), bf16_lo(rv.z), bf16_hi(rv.z), bf16_lo(rv.w), bf16_hi(rv.w)};
+                if (a.res_mode == 0) {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) f[i] += rf[i];
+                } else {  // activation backward of the layer below, fused: multiply by act'(its saved output)
+                  const float slope = a.res_mode == 1 ? 0.f : 0.2f;
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) f[i] = rf[i] > 0.f ? f[i] : f[i] * slope;
+                }
               } else {
                 const float* rp = reinterpret_cast<const float*>(a.res) + pix * a.res_pitch + jg;
 #pragma unroll
@@ -589,13 +413,96 @@ __global__ void __launch_bounds__(kThreadsC, 1) conv_igemm_kernel(const __grid_c
             }
           }
         }
-      }  // (the SPADE epilogue always writes bf16 NHWC: it only exists in the staged form above)
+      } else {
+        // ---------------- SPADE: 16 GEMM columns = 8 channels of (gamma, beta)
+        // The x (and noise) loads do not depend on the accumulator: all of this warp's chunks issue them BEFORE waiting for the MMAs
+        // of the tile, so their DRAM/L2 latency overlaps the mainloop instead of sitting on the epilogue's critical path (the ncu
+        // source view of round 1 showed the epilogue warps stalled on the first use of x; profiles/r2_conv_stall_*.txt).
+        constexpr int kMaxChunks = (256 / 16 + kEpiC - 1) / kEpiC;  // BN <= 256: at most 6 chunks of 16 columns per warpgroup
+        const int sh0 = a.x0_shift;
+        const long long pix0 = ((long long)n * (a.Hout >> sh0) + (y >> sh0)) * (a.Wout >> sh0) + (x >> sh0);
+        uint4 xv[kMaxChunks];
+#pragma unroll
+        for (int k = 0; k < kMaxChunks; ++k) {
+          const int col = wg * 16 + k * 16 * kEpiC;
+          const int c0 = (n_base + col) >> 1;
+          xv[k] = make_uint4(0, 0, 0, 0);
+          if (col < a.BN && valid && c0 < a.C_mod) {
+            const __nv_bfloat16* xp = (c0 < a.x0_c) ? (a.x0 + pix0 * a.x0_pitch + c0)
+                                                     : (a.x1 + pix * a.x1_pitch + (c0 - a.x0_c));
+            xv[k] = __ldg(reinterpret_cast<const uint4*>(xp));
+          }
+        }
+        const float nz = (valid && a.noise) ? __ldg(a.noise + pix) : 0.f;
+        mbar_wait_acct(bar_tfull(acc), aph, acct, w0);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < kMaxChunks; ++k) {
+          const int col = wg * 16 + k * 16 * kEpiC;
+          if (col >= a.BN) break;
+          const int c0 = (n_base + col) >> 1;
+          const bool live = valid && c0 < a.C_mod;
+          // per-channel constants: warp-uniform addresses, L1-resident after the first tile of an image
+          float mu[8], rs[8], nsv[8], sh[16];
+          if (live) {
+            const float4* mp = reinterpret_cast<const float4*>(a.mean + (long long)n * a.C_mod + c0);
+            const float4* rp = reinterpret_cast<const float4*>(a.rstd + (long long)n * a.C_mod + c0);
+            *reinterpret_cast<float4*>(mu) = __ldg(mp);
+            *reinterpret_cast<float4*>(mu + 4) = __ldg(mp + 1);
+            *reinterpret_cast<float4*>(rs) = __ldg(rp);
+            *reinterpret_cast<float4*>(rs + 4) = __ldg(rp + 1);
+            if (a.noise_scale) {
+              const float4* np_ = reinterpret_cast<const float4*>(a.noise_scale + c0);
+              *reinterpret_cast<float4*>(nsv) = __ldg(np_);
+              *reinterpret_cast<float4*>(nsv + 4) = __ldg(np_ + 1);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) nsv[i] = 0.f;
+            }
+            if (a.shift) {
+              const float4* sp = reinterpret_cast<const float4*>(a.shift + 2 * c0);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(sh + 4 * i) = __ldg(sp + i);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) sh[i] = 0.f;
+            }
+          }
+          uint32_t v[16];
+          __syncwarp();
+          tmem_ld16(taddr + col, v);
+          tmem_wait_ld();
+          if (!live) continue;
+          const uint4 xk = xv[k];
+          const float xs[8] = {bf16_lo(xk.x), bf16_hi(xk.x), bf16_lo(xk.y), bf16_hi(xk.y),
+                               bf16_lo(xk.z), bf16_hi(xk.z), bf16_lo(xk.w), bf16_hi(xk.w)};
+          float o[8], gmv[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float xval = fmaf(nz, nsv[i], xs[i]);
+            const float gm = __uint_as_float(v[2 * i]) + sh[2 * i];
+            const float bt = __uint_as_float(v[2 * i + 1]) + sh[2 * i + 1];
+            const float xn = (xval - mu[i]) * rs[i];
+            gmv[i] = gm;
+            o[i] = apply_act(fmaf(xn, 1.f + gm, bt), a.act);
+          }
+          if (a.gamma_out) {  // training: keep gamma for the backward pass (saves re-running this GEMM)
+            uint4 gv;
+            gv.x = pack_bf16(gmv[0], gmv[1]); gv.y = pack_bf16(gmv[2], gmv[3]);
+            gv.z = pack_bf16(gmv[4], gmv[5]); gv.w = pack_bf16(gmv[6], gmv[7]);
+            *reinterpret_cast<uint4*>(a.gamma_out + pix * a.gamma_pitch + c0) = gv;
+          }
+          uint4 ov;
+          ov.x = pack_bf16(o[0], o[1]); ov.y = pack_bf16(o[2], o[3]);
+          ov.z = pack_bf16(o[4], o[5]); ov.w = pack_bf16(o[6], o[7]);
+          *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) + pix * a.out_pitch + c0) = ov;
+        }
+      }
       __syncwarp();
       tc_fence_before();
       mbar_arrive(bar_tempty(acc));
       if (++acc == NACC) { acc = 0; aph ^= 1u; }
     }
-    if (a.stage_out && r == 0) bulk_wait_read<0>();  // the last TMA store must have drained its staging tile before the CTA exits
     if (acct && warp == 4 && lane == 0) {  // first epilogue warp: time stalled on the accumulator vs total
       a.stats[blockIdx.x * 16 + 6] = w0;
       a.stats[blockIdx.x * 16 + 7] = (unsigned long long)(clock64() - t_begin);
@@ -807,8 +714,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_pixn_kernel(const __grid_con
           const int n = (ti << sub_shift) + (rr >> (a.tw_log + a.th_log));
           if (x < a.Wout && y < a.Hout && n < a.Nimg) {
             const long long pix = ((long long)n * a.Hout + y) * a.Wout + x;
-            *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) + pix * a.out_pitch + c8 * 8) =
-                *reinterpret_cast<const uint4*>(T + pl * sc_n + c8 * 8);
+            uint4 o = *reinterpret_cast<const uint4*>(T + pl * sc_n + c8 * 8);
+            if (a.res_mode) {  // fused activation backward of the layer below: out *= act'(res), res = that layer's saved output
+              const uint4 gq = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(a.res) + pix * a.res_pitch + c8 * 8));
+              const float slope = a.res_mode == 1 ? 0.f : 0.2f;
+              const uint32_t gw[4] = {gq.x, gq.y, gq.z, gq.w};
+              uint32_t ow[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float lo = bf16_lo(gw[i]) > 0.f ? bf16_lo(ow[i]) : bf16_lo(ow[i]) * slope;
+                const float hi = bf16_hi(gw[i]) > 0.f ? bf16_hi(ow[i]) : bf16_hi(ow[i]) * slope;
+                ow[i] = pack_bf16(lo, hi);
+              }
+              o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+            }
+            *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) + pix * a.out_pitch + c8 * 8) = o;
           }
           pl += step_pl;
           c8 += step_c8;
@@ -914,7 +834,7 @@ extern "C" int hrv_conv2d_fwd(const hrv_conv_params* p, hrv_stream stream) {
   // Pixel-N variant (weights as the M operand, 256 pixels as N): few output channels, plain bf16 NHWC output.
   const char* env_pixn = getenv("HRV_CONV_PIXN");  // read per call: tests flip it to compare the two kernels on identical inputs
   const bool pixn = !(env_pixn && env_pixn[0] == '0') && p->epi == HRV_EPI_LINEAR && p->bk == 64 && p->n_gemm <= 128 &&
-                    out.dtype == HRV_BF16 && p->out_layout == HRV_NHWC && !p->res.ptr && in.c > 32 &&
+                    out.dtype == HRV_BF16 && p->out_layout == HRV_NHWC && (!p->res.ptr || p->res_mode != 0) && in.c > 32 &&
                     ((out.c + 7) & ~7) <= out.pitch && ((out.c + 7) & ~7) <= 128;
   // Halo mode (one (16+KH-1)x(8+KW-1) box per channel chunk, taps as shifted descriptor views) whenever the image is
   // tall enough for a 16x8 single-image tile; tap-by-tap mode (tile may span images) for the tiny pyramid levels.
@@ -940,7 +860,10 @@ extern "C" int hrv_conv2d_fwd(const hrv_conv_params* p, hrv_stream stream) {
   a.epi = p->epi; a.act = p->act;
   a.scale = p->scale; a.shift = p->shift;
   a.out = out.ptr; a.out_pitch = out.pitch; a.out_dtype = out.dtype; a.out_layout = p->out_layout; a.out_c = out.c;
-  a.res = p->res.ptr; a.res_pitch = p->res.pitch; a.res_dtype = p->res.dtype;
+  a.res = p->res.ptr; a.res_pitch = p->res.pitch; a.res_dtype = p->res.dtype; a.res_mode = p->res.ptr ? p->res_mode : 0;
+  if (a.res_mode < 0 || a.res_mode > 2) return set_error(HRV_EINVAL, "conv: res_mode %d", a.res_mode);
+  if (a.res_mode && (p->res.dtype != HRV_BF16 || out.dtype != HRV_BF16 || p->out_layout != HRV_NHWC || p->epi != HRV_EPI_LINEAR || p->act != HRV_ACT_NONE))
+    return set_error(HRV_EINVAL, "conv: gate modes need a bf16 res, a bf16 NHWC output, the LINEAR epilogue and no activation");
 
   if (p->epi == HRV_EPI_SPADE) {
     const int C = p->x0.c + (p->x1.ptr ? p->x1.c : 0);
@@ -965,21 +888,11 @@ extern "C" int hrv_conv2d_fwd(const hrv_conv_params* p, hrv_stream stream) {
     return set_error(HRV_EINVAL, "conv: unknown epilogue %d", p->epi);
   }
 
-  // ---- staged epilogue (classic kernel, bf16 NHWC output): per-warpgroup staging tiles + TMA stores
-  const bool stage_out = !pixn && out.dtype == HRV_BF16 && p->out_layout == HRV_NHWC;
-  uint32_t staging = 0;
-  if (stage_out) {
-    a.stage_out = 1;
-    a.epi_off = 2048u;
-    a.epi_buf_bytes = 128u * (p->epi == HRV_EPI_SPADE ? 64u : 128u);
-    a.epi_wg_bytes = a.epi_buf_bytes * ((p->epi == HRV_EPI_SPADE && p->gamma_out.ptr) ? 2u : 1u);
-    staging = (uint32_t)kEpiC * a.epi_wg_bytes;
-  }
   // ---- pipeline geometry
   const int elem = 2;
   const int taps = p->kh * p->kw;
   const uint32_t row_bytes = p->bk * 2;
-  const uint32_t budget = 225u * 1024u - 3072u - staging;  // 1 KB alignment slack + 2 KB control block + epilogue staging
+  const uint32_t budget = 225u * 1024u - 3072u;  // 1 KB alignment slack + 2 KB control block
   const int LP = TW + p->kw - 1, HRows = (TH + p->kh - 1) * LP;
   int tpb = 1;
   if (halo) {
@@ -1037,30 +950,6 @@ extern "C" int hrv_conv2d_fwd(const hrv_conv_params* p, hrv_stream stream) {
     int rc = encode_tensor_map(&a.tmB, 3, const_cast<void*>(p->wpack), dims, strides, box, es, sw);
     if (rc) return rc;
   }
-  if (stage_out) {
-    const bool sp = p->epi == HRV_EPI_SPADE;
-    const CUtensorMapSwizzle osw = sp ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
-    cuuint32_t box[4] = {(cuuint32_t)(sp ? 32 : 64), (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TN};
-    a.tail_cols = p->bn % 64;
-    cuuint32_t tbox[4] = {(cuuint32_t)(sp ? a.tail_cols / 2 : a.tail_cols), (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TN};
-    cuuint32_t es[4] = {1, 1, 1, 1};
-    {
-      cuuint64_t dims[4] = {(cuuint64_t)((out.c + 7) & ~7), (cuuint64_t)out.w, (cuuint64_t)out.h, (cuuint64_t)out.n};
-      cuuint64_t strides[3] = {(cuuint64_t)out.pitch * elem, (cuuint64_t)out.w * out.pitch * elem, (cuuint64_t)out.h * out.w * out.pitch * elem};
-      int rc = encode_tensor_map(&a.tmOut, 4, out.ptr, dims, strides, box, es, osw);
-      if (rc) return rc;
-      if (a.tail_cols && (rc = encode_tensor_map(&a.tmOutT, 4, out.ptr, dims, strides, tbox, es, CU_TENSOR_MAP_SWIZZLE_NONE))) return rc;
-    }
-    if (sp && p->gamma_out.ptr) {
-      const hrv_tensor& g = p->gamma_out;
-      if (g.n != out.n || g.h != out.h || g.w != out.w) return set_error(HRV_EINVAL, "conv(spade): gamma_out extent mismatch");
-      cuuint64_t dims[4] = {(cuuint64_t)((g.c + 7) & ~7), (cuuint64_t)g.w, (cuuint64_t)g.h, (cuuint64_t)g.n};
-      cuuint64_t strides[3] = {(cuuint64_t)g.pitch * elem, (cuuint64_t)g.w * g.pitch * elem, (cuuint64_t)g.h * g.w * g.pitch * elem};
-      int rc = encode_tensor_map(&a.tmGam, 4, g.ptr, dims, strides, box, es, osw);
-      if (rc) return rc;
-      if (a.tail_cols && (rc = encode_tensor_map(&a.tmGamT, 4, g.ptr, dims, strides, tbox, es, CU_TENSOR_MAP_SWIZZLE_NONE))) return rc;
-    }
-  }
   cudaStream_t st = (cudaStream_t)stream;
   if (pixn) {
     a.tiles_m = a.tiles_x * a.tiles_y * a.tiles_img;
@@ -1076,7 +965,7 @@ extern "C" int hrv_conv2d_fwd(const hrv_conv_params* p, hrv_stream stream) {
     if (a.pairs < gridp) gridp = a.pairs;
     return launch_pixn(a, gridp, smem_p, st);
   }
-  size_t smem = 3072 + staging + (halo ? (size_t)a.stages * a.a_stage_bytes + (size_t)a.sb_stages * a.b_stage_bytes
+  size_t smem = 3072 + (halo ? (size_t)a.stages * a.a_stage_bytes + (size_t)a.sb_stages * a.b_stage_bytes
                              : (size_t)a.stages * (128 * row_bytes + (((uint32_t)p->bn * row_bytes + 1023u) & ~1023u)));
   if (smem < 120 * 1024) smem = 120 * 1024;  // force one CTA per SM (TMEM: up to 512 columns per CTA)
 

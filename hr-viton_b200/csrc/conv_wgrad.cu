@@ -6,8 +6,9 @@
 // sit LBO bytes apart, 8-row K atoms SBO = 1024 B apart (layout probed on B200: tools/umma_mnmajor_probe.cu).
 // The kx taps are *shifted views* of one X box of PX+KW-1 pixels (descriptor start + kx rows; absolute-address swizzle), so per
 // 64-pixel chunk one dY box and one X box feed KW*4 MMAs of 128 x BN x 16.
-// Grid = (co tiles) x (ci tiles) x KH x splits; each CTA streams its share of the (n, y, x-segment) chunks and finally adds its
-// fp32 partial tile into dW with red.global.add (dW is zeroed by the caller).
+// Grid = (co tiles) x (ci tiles) x KH x splits; each CTA streams its share of the (n, y, x-segment) chunks and finally writes its fp32
+// partial tile into slab `split` of the workspace [splits][cout][cin][KH][KW]; wgrad_reduce_kernel then sums the slabs in a FIXED
+// order into dW — the result is bit-reproducible run to run (round 1 accumulated with fp32 atomics, whose order is not).
 // Replaces the weight-gradient half of nn.Conv2d's backward (networks.py / network_generator.py convolutions, stage-2 training).
 #include <stdlib.h>
 
@@ -26,8 +27,27 @@ struct alignas(64) WgradArgs {
   int KH, KW, pad;
   int cout, cin, BN, stages, splits;
   int m_tiles, n_tiles;
-  float* dw;  // (cout, cin, KH, KW) fp32
+  float* dw;  // (cout, cin, KH, KW) fp32 (splits == 1: written directly) or the workspace [splits][cout][cin][KH][KW]
 };
+
+// dw[i] = sum_{s < splits} ws[s][i], slabs added in increasing s: deterministic.  float4 per thread.
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, long long n4, long long slab4, int splits) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 acc = __ldg(reinterpret_cast<const float4*>(ws) + i);
+  for (int s = 1; s < splits; ++s) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(ws) + (long long)s * slab4 + i);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  reinterpret_cast<float4*>(dw)[i] = acc;
+}
+__global__ void __launch_bounds__(256) wgrad_reduce1_kernel(const float* __restrict__ ws, float* __restrict__ dw, long long n, int splits) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float acc = __ldg(ws + i);
+  for (int s = 1; s < splits; ++s) acc += __ldg(ws + (long long)s * n + i);
+  dw[i] = acc;
+}
 
 __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_kernel(const __grid_constant__ WgradArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -126,6 +146,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_kernel(const __grid_
     // ===================================================== epilogue: fp32 partial tile -> red.add into dW[(co*cin+ci)*KH*KW + ky*KW + kx]
     const int q = warp & 3;  // warps 2,3,4,5 -> TMEM lane quarters 2,3,0,1
     const int co = m0 + q * 32 + lane;
+    float* const slab = a.dw + (long long)split * a.cout * a.cin * a.KH * a.KW;  // this CTA's private slab: plain stores, no atomics
     if (my_chunks > 0) {
       mbar_wait(bar_done, 0);
       tc_fence_after();
@@ -139,11 +160,14 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_kernel(const __grid_
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const int ci = n0 + col + j;
-              if (ci < a.cin) atomicAdd(a.dw + (((long long)co * a.cin + ci) * a.KH + ky) * a.KW + kx, __uint_as_float(v[j]));
+              if (ci < a.cin) slab[(((long long)co * a.cin + ci) * a.KH + ky) * a.KW + kx] = __uint_as_float(v[j]);
             }
           }
         }
       }
+    } else if (co < a.cout) {  // a split without work (more splits than chunks): its slab entries are zeros
+      for (int kx = 0; kx < a.KW; ++kx)
+        for (int ci = n0; ci < n0 + a.BN && ci < a.cin; ++ci) slab[(((long long)co * a.cin + ci) * a.KH + ky) * a.KW + kx] = 0.f;
     }
   }
   tc_fence_before();
@@ -155,8 +179,44 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_kernel(const __grid_
 
 using namespace hrv;
 
+// Split-K factor: one CTA per SM is resident (512 TMEM columns each), CTAs of one launch take equal time, so the launch costs
+// waves * (chunks per CTA + fixed prologue/epilogue) with waves = ceil(grid / SMs).  Pick the split that minimises it — a grid
+// that spills a few CTAs into an extra wave (e.g. 300 CTAs on 148 SMs) costs a whole wave.
+static int wgrad_splits(int tiles, int chunks) {
+  const int sms = sm_count();
+  int splits = 1;
+  const long long kFixed = 16;  // prologue + TMEM read-out + epilogue, in units of one 64-pixel chunk step
+  long long best = -1;
+  int smax = 8 * sms / tiles + 1;
+  if (smax > chunks) smax = chunks;
+  if (smax < 1) smax = 1;
+  for (int sp = 1; sp <= smax; ++sp) {
+    const long long waves = ((long long)tiles * sp + sms - 1) / sms;
+    const long long cost = waves * ((chunks + sp - 1) / sp + kFixed);
+    if (best < 0 || cost < best) { best = cost; splits = sp; }
+  }
+  const char* env = getenv("HRV_WGRAD_SPLITS");  // A/B runs
+  if (env && atoi(env) > 0) splits = atoi(env) < chunks ? atoi(env) : (chunks > 0 ? chunks : 1);
+  return splits;
+}
+static void wgrad_geometry(const hrv_tensor* x, const hrv_tensor* dy, int kh, int* tiles, int* chunks, int* bn, int* m_tiles, int* n_tiles) {
+  *bn = x->c <= 64 ? 64 : 128;
+  *m_tiles = (dy->c + 127) / 128;
+  *n_tiles = (x->c + *bn - 1) / *bn;
+  *chunks = x->n * dy->h * ((dy->w + kPX - 1) / kPX);
+  *tiles = *m_tiles * *n_tiles * kh;
+}
+
+extern "C" size_t hrv_conv2d_wgrad_workspace_bytes(const hrv_tensor* x, const hrv_tensor* dy, int32_t kh, int32_t kw) {
+  if (!x || !dy || kh < 1 || kw < 1) return 0;
+  int tiles, chunks, bn, mt, nt;
+  wgrad_geometry(x, dy, kh, &tiles, &chunks, &bn, &mt, &nt);
+  const int splits = wgrad_splits(tiles, chunks);
+  return splits > 1 ? (size_t)splits * dy->c * x->c * kh * kw * sizeof(float) : 0;
+}
+
 extern "C" int hrv_conv2d_wgrad(const hrv_tensor* x, const hrv_tensor* dy, int32_t kh, int32_t kw, int32_t pad, float* dw,
-                                hrv_stream stream) {
+                                void* workspace, size_t workspace_bytes, hrv_stream stream) {
   if (!x || !dy || !x->ptr || !dy->ptr || !dw) return set_error(HRV_EINVAL, "wgrad: null argument");
   if (x->dtype != HRV_BF16 || dy->dtype != HRV_BF16) return set_error(HRV_EINVAL, "wgrad: x and dy must be bf16 NHWC");
   if (((uintptr_t)x->ptr & 15) || ((uintptr_t)dy->ptr & 15) || (x->pitch % 8) || (dy->pitch % 8))
@@ -167,30 +227,17 @@ extern "C" int hrv_conv2d_wgrad(const hrv_tensor* x, const hrv_tensor* dy, int32
   memset(&a, 0, sizeof(a));
   a.Nimg = x->n; a.OH = dy->h; a.OW = dy->w; a.xsegs = (dy->w + kPX - 1) / kPX;
   a.KH = kh; a.KW = kw; a.pad = pad; a.cout = dy->c; a.cin = x->c;
-  a.BN = x->c <= 64 ? 64 : 128;
-  a.m_tiles = (dy->c + 127) / 128;
-  a.n_tiles = (x->c + a.BN - 1) / a.BN;
-  a.dw = dw;
-  const int chunks = a.Nimg * a.OH * a.xsegs;
-  const int tiles = a.m_tiles * a.n_tiles * kh;
-  // Split-K factor: one CTA per SM is resident (512 TMEM columns each), CTAs of one launch take equal time, so the launch costs
-  // waves * (chunks per CTA + fixed prologue/epilogue) with waves = ceil(grid / SMs).  Pick the split that minimises it — a grid
-  // that spills a few CTAs into an extra wave (e.g. 300 CTAs on 148 SMs) costs a whole wave.
-  const int sms = sm_count();
-  int splits = 1;
-  {
-    const long long kFixed = 16;  // prologue + TMEM read-out + red.global epilogue, in units of one 64-pixel chunk step
-    long long best = -1;
-    int smax = 8 * sms / tiles + 1;
-    if (smax > chunks) smax = chunks;
-    if (smax < 1) smax = 1;
-    for (int sp = 1; sp <= smax; ++sp) {
-      const long long waves = ((long long)tiles * sp + sms - 1) / sms;
-      const long long cost = waves * ((chunks + sp - 1) / sp + kFixed);
-      if (best < 0 || cost < best) { best = cost; splits = sp; }
-    }
-    const char* env = getenv("HRV_WGRAD_SPLITS");  // A/B runs
-    if (env && atoi(env) > 0) splits = atoi(env) < chunks ? atoi(env) : chunks;
+  int tiles, chunks;
+  wgrad_geometry(x, dy, kh, &tiles, &chunks, &a.BN, &a.m_tiles, &a.n_tiles);
+  const int splits = wgrad_splits(tiles, chunks);
+  const long long dw_elems = (long long)dy->c * x->c * kh * kw;
+  if (splits > 1) {
+    const size_t need = (size_t)splits * dw_elems * sizeof(float);
+    if (!workspace || workspace_bytes < need || ((uintptr_t)workspace & 15))
+      return set_error(HRV_EINVAL, "wgrad: workspace too small or misaligned (%zu < %zu): ask hrv_conv2d_wgrad_workspace_bytes", workspace_bytes, need);
+    a.dw = (float*)workspace;  // CTAs write slabs; wgrad_reduce_kernel sums them into dw in a fixed order
+  } else {
+    a.dw = dw;                 // one CTA per output element: plain stores straight into dw
   }
   a.splits = splits;
   const uint32_t stage_bytes = 2u * kPX * 128u + ((((uint32_t)(kPX + kw - 1) * 128u + 1023u) & ~1023u) * (uint32_t)(a.BN / 64));
@@ -225,5 +272,15 @@ extern "C" int hrv_conv2d_wgrad(const hrv_tensor* x, const hrv_tensor* dy, int32
   conv_wgrad_kernel<<<grid, kWgThreads, smem, (cudaStream_t)stream>>>(a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(HRV_ECUDA, "conv_wgrad launch: %s", cudaGetErrorString(e));
+  if (splits > 1) {
+    if ((dw_elems % 4) || ((uintptr_t)dw & 15)) {  // slabs not 16-byte aligned: scalar reduction (tiny layers, e.g. 13 -> 13 channels)
+      wgrad_reduce1_kernel<<<(unsigned)((dw_elems + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const float*)workspace, dw, dw_elems, splits);
+    } else {
+      const long long n4 = dw_elems / 4;
+      wgrad_reduce_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const float*)workspace, dw, n4, n4, splits);
+    }
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error(HRV_ECUDA, "wgrad_reduce launch: %s", cudaGetErrorString(e));
+  }
   return HRV_OK;
 }

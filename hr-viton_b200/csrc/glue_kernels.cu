@@ -69,7 +69,7 @@ __global__ void maxpool2_fwd_kernel(GView x, GView y, int G, long long total) {
   st16(at_w(y, n, Y, X) + g * 8, pk8(o));
 }
 // The gradient goes to the FIRST maximum of the window in row-major order (what the library's index-based backward does).
-__global__ void maxpool2_bwd_kernel(GView x, GView dy, GView dx, int G, long long total) {
+__global__ void maxpool2_bwd_kernel(GView x, GView dy, GView dx, int G, long long total, int relu_gate) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int g = (int)(idx % G);
@@ -88,7 +88,7 @@ __global__ void maxpool2_bwd_kernel(GView x, GView dy, GView dx, int G, long lon
     for (int k = 1; k < 4; ++k)
       if (f[k][i] > m) { m = f[k][i]; best = k; }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) o[k][i] = (k == best) ? gy[i] : 0.f;
+    for (int k = 0; k < 4; ++k) o[k][i] = (k == best && !(relu_gate && m <= 0.f)) ? gy[i] : 0.f;
   }
   __nv_bfloat16* q = at_w(dx, n, 2 * Y, 2 * X) + g * 8;
   const long long qrow = (long long)dx.w * dx.pitch;
@@ -403,7 +403,7 @@ __global__ void __launch_bounds__(256) l1_fwd_kernel(GView a, GView b, int G, lo
     atomicAdd(out, t);
   }
 }
-__global__ void l1_bwd_kernel(GView a, GView b, GView da, int G, long long total, const float* __restrict__ gscale) {
+__global__ void l1_bwd_kernel(GView a, GView b, GView da, int G, long long total, const float* __restrict__ gscale, int relu_gate) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int g = (int)(idx % G);
@@ -416,7 +416,7 @@ __global__ void l1_bwd_kernel(GView a, GView b, GView da, int G, long long total
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const float d = fa[i] - fb[i];
-    o[i] = (i < lim) ? (d > 0.f ? gs : (d < 0.f ? -gs : 0.f)) : 0.f;
+    o[i] = (i < lim && !(relu_gate && fa[i] <= 0.f)) ? (d > 0.f ? gs : (d < 0.f ? -gs : 0.f)) : 0.f;
   }
   st16(reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(da.ptr)) + pix * da.pitch + g * 8, pk8(o));
 }
@@ -447,7 +447,7 @@ extern "C" int hrv_maxpool2_fwd(const hrv_tensor* x, const hrv_tensor* y, hrv_st
   return launched("maxpool2_fwd");
 }
 
-extern "C" int hrv_maxpool2_bwd(const hrv_tensor* x, const hrv_tensor* dy, const hrv_tensor* dx, hrv_stream stream) {
+extern "C" int hrv_maxpool2_bwd(const hrv_tensor* x, const hrv_tensor* dy, const hrv_tensor* dx, int32_t relu_gate, hrv_stream stream) {
   int rc;
   if ((rc = check_vec(x, "maxpool_bwd x")) || (rc = check_vec(dy, "maxpool_bwd dy")) || (rc = check_vec(dx, "maxpool_bwd dx"))) return rc;
   if (dy->n != x->n || dy->h != x->h / 2 || dy->w != x->w / 2 || dy->c != x->c || dx->n != x->n || dx->h != x->h || dx->w != x->w || dx->c != x->c)
@@ -458,7 +458,7 @@ extern "C" int hrv_maxpool2_bwd(const hrv_tensor* x, const hrv_tensor* dy, const
   }
   const int G = (x->c + 7) / 8;
   const long long total = (long long)dy->n * dy->h * dy->w * G;
-  if (total) maxpool2_bwd_kernel<<<nblocks(total, 256), 256, 0, (cudaStream_t)stream>>>(gv(x), gv(dy), gv(dx), G, total);
+  if (total) maxpool2_bwd_kernel<<<nblocks(total, 256), 256, 0, (cudaStream_t)stream>>>(gv(x), gv(dy), gv(dx), G, total, relu_gate);
   return launched("maxpool2_bwd");
 }
 
@@ -574,12 +574,12 @@ extern "C" int hrv_l1_sum(const hrv_tensor* a, const hrv_tensor* b, double* sum,
   return launched("l1_sum");
 }
 
-extern "C" int hrv_l1_bwd(const hrv_tensor* a, const hrv_tensor* b, const float* gscale, const hrv_tensor* da, hrv_stream stream) {
+extern "C" int hrv_l1_bwd(const hrv_tensor* a, const hrv_tensor* b, const float* gscale, const hrv_tensor* da, int32_t relu_gate, hrv_stream stream) {
   int rc;
   if ((rc = l1_check(a, b)) || (rc = l1_check(a, da))) return rc;
   if (!gscale) return set_error(HRV_EINVAL, "l1_bwd: null gscale");
   const int G = (a->c + 7) / 8;
   const long long total = (long long)a->n * a->h * a->w * G;
-  if (total) l1_bwd_kernel<<<nblocks(total, 256), 256, 0, (cudaStream_t)stream>>>(gv(a), gv(b), gv(da), G, total, gscale);
+  if (total) l1_bwd_kernel<<<nblocks(total, 256), 256, 0, (cudaStream_t)stream>>>(gv(a), gv(b), gv(da), G, total, gscale, relu_gate);
   return launched("l1_bwd");
 }

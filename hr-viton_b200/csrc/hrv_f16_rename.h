@@ -30,3 +30,4 @@
 #define hrv_flow_warp_nchw hrv_flow_warp_nchw_f16
 #define hrv_instnorm_stats2 hrv_instnorm_stats2_f16
 #define hrv_onehot_u8 hrv_onehot_u8_f16
+#define hrv_conv2d_wgrad_workspace_bytes hrv_conv2d_wgrad_workspace_bytes_f16

@@ -222,7 +222,7 @@ def pack_s2d(w, pad):
 
 # ----------------------------------------------------------------------------------------------- ops
 
-def conv2d(inp, pw, out, act=ACT_NONE, scale=None, shift=None, res=None, out_layout=capi.NHWC):
+def conv2d(inp, pw, out, act=ACT_NONE, scale=None, shift=None, res=None, out_layout=capi.NHWC, res_mode=capi.RES_ADD):
     assert inp.c == pw.cin, (inp.c, pw.cin)
     p = capi.ConvParams()
     p.inp = inp.ct()
@@ -240,6 +240,7 @@ def conv2d(inp, pw, out, act=ACT_NONE, scale=None, shift=None, res=None, out_lay
     p.scale = _p(scale)
     p.shift = _p(shift)
     p.res = res.ct() if res is not None else _NULL
+    p.res_mode = res_mode if res is not None else 0
     p.x0 = _NULL
     p.x1 = _NULL
     p.gamma_out = _NULL
@@ -262,6 +263,7 @@ def conv2d_spade(actv, pw, out, x0, x0_shift, x1, mean, rstd, noise, noise_scale
     p.scale = None
     p.shift = _p(shift)
     p.res = _NULL
+    p.res_mode = 0
     p.x0 = x0.ct()
     p.x1 = x1.ct() if x1 is not None else _NULL
     p.x0_shift = x0_shift
@@ -356,11 +358,11 @@ def maxpool2(x):
     return y
 
 
-def maxpool2_bwd(x, dy):
+def maxpool2_bwd(x, dy, relu_gate=False):
     dx = Act.empty(x.n, x.h, x.w, x.c, pitch=x.pitch if x.c0 == 0 else None)
     tx, tdy, tdx = x.ct(), dy.ct(), dx.ct()
     with _Timed("glue", 0.0, label="maxpool2_bwd"):
-        capi.check(_L(x).hrv_maxpool2_bwd(ctypes.byref(tx), ctypes.byref(tdy), ctypes.byref(tdx), _stream()), "maxpool2_bwd")
+        capi.check(_L(x).hrv_maxpool2_bwd(ctypes.byref(tx), ctypes.byref(tdy), ctypes.byref(tdx), 1 if relu_gate else 0, _stream()), "maxpool2_bwd")
     return dx
 
 
@@ -393,12 +395,12 @@ def l1_sum(a, b):
     return out
 
 
-def l1_bwd(a, b, gscale):
-    """da = sign(a - b) * gscale (gscale: 1-element fp32 cuda tensor)."""
+def l1_bwd(a, b, gscale, relu_gate=False):
+    """da = sign(a - b) * gscale (gscale: 1-element fp32 cuda tensor); relu_gate: times (a > 0)."""
     da = Act.empty(a.n, a.h, a.w, a.c, pitch=a.pitch if a.c0 == 0 else None)
     ta, tb, td = a.ct(), b.ct(), da.ct()
     with _Timed("glue", 0.0, label="l1_bwd"):
-        capi.check(_L(a).hrv_l1_bwd(ctypes.byref(ta), ctypes.byref(tb), gscale.data_ptr(), ctypes.byref(td), _stream()), "l1_bwd")
+        capi.check(_L(a).hrv_l1_bwd(ctypes.byref(ta), ctypes.byref(tb), gscale.data_ptr(), ctypes.byref(td), 1 if relu_gate else 0, _stream()), "l1_bwd")
     return da
 
 
@@ -582,11 +584,14 @@ def act_bwd_bias(dy, y, act, want_dv=True, want_bias=True):
 
 def conv2d_wgrad(x, dy, kh, kw, pad):
     """dW (cout,cin,kh,kw) fp32 of a stride-1 convolution, on tcgen05 (hrv_conv2d_wgrad)."""
-    dw = torch.zeros((dy.c, x.c, kh, kw), dtype=torch.float32, device=x.buf.device)
+    dw = torch.empty((dy.c, x.c, kh, kw), dtype=torch.float32, device=x.buf.device)
     tx, tdy = x.ct(), dy.ct()
-    with _Timed("wgrad", 2.0 * x.c * dy.c * kh * kw * dy.n * dy.h * dy.w,
+    L = _L(x)
+    nws = int(L.hrv_conv2d_wgrad_workspace_bytes(ctypes.byref(tx), ctypes.byref(tdy), kh, kw))
+    ws = torch.empty(nws, dtype=torch.uint8, device=x.buf.device) if nws else None  # split-K slabs, summed in a fixed order (deterministic)
+    with _Timed("wgrad", 2.0 * x.c * dy.c * kh * kw * dy.n * dy.h * dy.w, launches=2 if nws else 1,
                 label="%d->%d k%dx%d n%d %dx%d" % (x.c, dy.c, kh, kw, dy.n, dy.h, dy.w)):
-        capi.check(_L(x).hrv_conv2d_wgrad(ctypes.byref(tx), ctypes.byref(tdy), kh, kw, pad, dw.data_ptr(), _stream()), "conv2d_wgrad")
+        capi.check(L.hrv_conv2d_wgrad(ctypes.byref(tx), ctypes.byref(tdy), kh, kw, pad, dw.data_ptr(), _p(ws), nws, _stream()), "conv2d_wgrad")
     return dw
 
 

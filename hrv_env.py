@@ -17,6 +17,18 @@ def install():
     for name, typ in (("float", float), ("int", int), ("bool", bool)):
         if not hasattr(np, name):
             setattr(np, name, typ)
+    import torch
+    if not getattr(torch.optim.Adam, "_hrv_betas_patch", False):
+        # train_generator.py:154,157 passes betas=(0, 0.9): an int next to a float, which torch >= 2.6 rejects ("betas must be either
+        # both floats or both Tensors") — an incompatibility between the 2022 script and today's torch, not with this repository
+        _init = torch.optim.Adam.__init__
+
+        def _adam_init(self, params, lr=1e-3, betas=(0.9, 0.999), *a, **k):
+            betas = tuple(b if torch.is_tensor(b) else float(b) for b in betas)
+            return _init(self, params, lr, betas, *a, **k)
+
+        torch.optim.Adam.__init__ = _adam_init
+        torch.optim.Adam._hrv_betas_patch = True
     if ROOT in sys.path:
         sys.path.remove(ROOT)
     sys.path.insert(0, ROOT)

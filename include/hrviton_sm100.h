@@ -34,6 +34,7 @@ enum hrv_dtype { HRV_BF16 = 0 /* = the flavour's 16-bit type: bf16 in hrv_<op>, 
 enum hrv_act { HRV_ACT_NONE = 0, HRV_ACT_RELU = 1, HRV_ACT_LRELU02 = 2, HRV_ACT_TANH = 3 };
 enum hrv_layout { HRV_NHWC = 0, HRV_NCHW = 1 };
 enum hrv_epilogue { HRV_EPI_LINEAR = 0, HRV_EPI_SPADE = 1 };
+enum hrv_res_mode { HRV_RES_ADD = 0, HRV_RES_GATE_RELU = 1, HRV_RES_GATE_LRELU = 2 };
 
 /* NHWC view: element (n,y,x,c) lives at ptr + (((n*h + y)*w + x)*pitch + c) elements.
  * For tensors read through TMA (conv inputs): bf16, ptr 16-byte aligned, pitch % 8 == 0. */
@@ -88,6 +89,10 @@ typedef struct hrv_conv_params {
   const float* noise; /* [N][H][W] or NULL */
   const float* noise_scale; /* [C] or NULL */
   hrv_tensor gamma_out; /* SPADE only, optional (ptr NULL = none): bf16 (n,h,w,C) receives gamma (incl. bias) for the backward pass */
+  int32_t res_mode;     /* what `res` does in the LINEAR epilogue: 0 (HRV_RES_ADD) v += res;  1 (HRV_RES_GATE_RELU) out = act(v) * (res > 0);
+                         * 2 (HRV_RES_GATE_LRELU) out = act(v) * (res > 0 ? 1 : 0.2).  The gate modes fuse the activation backward of the
+                         * layer BELOW into the data-gradient convolution of the layer above (res = that layer's saved output), so that
+                         * no separate dv = dy * act'(y) pass exists for ReLU chains such as Vgg19 (networks.py:201-231). */
 } hrv_conv_params;
 
 int hrv_conv2d_fwd(const hrv_conv_params* p, hrv_stream stream);
@@ -138,11 +143,15 @@ int hrv_norm_bwd_apply(const hrv_tensor* dxn, const hrv_tensor* src, int32_t shi
                        int32_t W, const float* noise, const float* noise_scale, const float* mean, const float* rstd,
                        const float* m1, const float* m2, const hrv_tensor* dx, double* dns, hrv_stream stream);
 
-/* Convolution weight gradient on tcgen05: dw[co][ci][ky][kx] += sum_{n,y,x} dy[n,y,x,co] * x[n,y+ky-pad,x+kx-pad,ci]
+/* Convolution weight gradient on tcgen05: dw[co][ci][ky][kx] = sum_{n,y,x} dy[n,y,x,co] * x[n,y+ky-pad,x+kx-pad,ci]
  * (stride 1; x: (n,h,w,cin), dy: (n,h+2pad-kh+1, w+2pad-kw+1, cout), both bf16 NHWC; kw <= 4). dw is fp32 in the reference's
- * parameter layout (cout,cin,kh,kw) and must be zeroed by the caller (partial tiles are accumulated with atomic adds).
+ * parameter layout (cout,cin,kh,kw) and is OVERWRITTEN.  The pixel (K) dimension is split over CTAs; each writes its partial tile
+ * into its own slab of `workspace` and a second kernel adds the slabs in a fixed order: the result is bit-reproducible run to run.
+ * workspace: hrv_conv2d_wgrad_workspace_bytes(...) bytes, 16-byte aligned (0 bytes when one CTA per output tile suffices).
  * The weight-gradient half of nn.Conv2d's backward for every convolution cited at hrv_conv2d_fwd. */
-int hrv_conv2d_wgrad(const hrv_tensor* x, const hrv_tensor* dy, int32_t kh, int32_t kw, int32_t pad, float* dw, hrv_stream stream);
+size_t hrv_conv2d_wgrad_workspace_bytes(const hrv_tensor* x, const hrv_tensor* dy, int32_t kh, int32_t kw);
+int hrv_conv2d_wgrad(const hrv_tensor* x, const hrv_tensor* dy, int32_t kh, int32_t kw, int32_t pad, float* dw, void* workspace,
+                     size_t workspace_bytes, hrv_stream stream);
 
 /* dv = dy * act'(y) on NHWC bf16 (dv optional) and bias_sum[c] = sum over all pixels of dv (fp64 [roundup8(C)], zeroed by the
  * call; optional): the activation backward + bias gradient of a conv epilogue act(conv + b) in one pass. */
@@ -199,9 +208,10 @@ int hrv_flow_warp_bwd(const float* flow_lo, const float* lin_x, const float* lin
 int hrv_space_to_depth_bwd(const hrv_tensor* d, const hrv_tensor* dx, hrv_stream stream);
 
 /* nn.MaxPool2d(2, 2) of Vgg19 (networks.py:201-231) on NHWC bf16: y = (n, h/2, w/2, c) (floor mode). The backward routes dy to
- * the first maximum of each window (recomputed from x; no index tensor). */
+ * the first maximum of each window (recomputed from x; no index tensor); relu_gate != 0 additionally multiplies by (x > 0), i.e. applies the
+ * ReLU backward of the convolution that produced x (see hrv_conv_params.res_mode). */
 int hrv_maxpool2_fwd(const hrv_tensor* x, const hrv_tensor* y, hrv_stream stream);
-int hrv_maxpool2_bwd(const hrv_tensor* x, const hrv_tensor* dy, const hrv_tensor* dx, hrv_stream stream);
+int hrv_maxpool2_bwd(const hrv_tensor* x, const hrv_tensor* dy, const hrv_tensor* dx, int32_t relu_gate, hrv_stream stream);
 
 /* Backward of hrv_avgpool3s2 (count_include_pad=False): dx (n,h,w,c) from dy (n,(h-1)/2+1,(w-1)/2+1,c). */
 int hrv_avgpool3s2_bwd(const hrv_tensor* dy, const hrv_tensor* dx, hrv_stream stream);
@@ -243,9 +253,10 @@ int hrv_flow_warp_nchw(const float* flow_lo, int32_t n, int32_t hl, int32_t wl, 
  * (network_generator.py:182-184) run as a single K=64 GEMM block (hrv_conv2d_fwd with kh=kw=1) and its weight gradient as a 1x1. */
 int hrv_im2col(const hrv_tensor* src, const hrv_tensor* dst, int32_t kh, int32_t kw, int32_t pad, hrv_stream stream);
 
-/* L1 feature loss (VGGLoss, networks.py:244-251): *sum = sum |a - b| over the views (fp64); da = sign(a - b) * (*gscale). */
+/* L1 feature loss (VGGLoss, networks.py:244-251): *sum = sum |a - b| over the views (fp64); da = sign(a - b) * (*gscale)
+ * (times (a > 0) when relu_gate != 0: the ReLU backward of the producer of a, fused). */
 int hrv_l1_sum(const hrv_tensor* a, const hrv_tensor* b, double* sum, hrv_stream stream);
-int hrv_l1_bwd(const hrv_tensor* a, const hrv_tensor* b, const float* gscale, const hrv_tensor* da, hrv_stream stream);
+int hrv_l1_bwd(const hrv_tensor* a, const hrv_tensor* b, const float* gscale, const hrv_tensor* da, int32_t relu_gate, hrv_stream stream);
 
 /* fp32 parameter (cout,cin,kh,kw) -> bf16 GEMM operand [kh*kw][n_pad][cin_k] of hrv_conv2d_fwd, zero padded, in one pass.
  * w1 (optional): second parameter of identical shape whose rows are interleaved with w0's (row 2c = w0[c], 2c+1 = w1[c]: the

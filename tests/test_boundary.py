@@ -93,7 +93,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(twins):
         assert hasattr(lib, name), "libhrviton_sm100.so does not export %s" % name
     for name in capi.FLAVOURED:  # twin prototypes are textually the main header's with the suffixed name
-        a = re.search(r"^int %s\(([^;]*?)\);" % name, hdr, flags=re.M | re.S).group(1)
-        b = re.search(r"^int %s_f16\(([^;]*?)\);" % name, hdr16, flags=re.M | re.S).group(1)
+        a = re.search(r"^(?:int|size_t) %s\(([^;]*?)\);" % name, hdr, flags=re.M | re.S).group(1)
+        b = re.search(r"^(?:int|size_t) %s_f16\(([^;]*?)\);" % name, hdr16, flags=re.M | re.S).group(1)
         assert a == b, name
     assert lib.hrv_version() >= 200

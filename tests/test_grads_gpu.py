@@ -393,3 +393,41 @@ def test_stage2_losses_match_oracle_pipeline():
     assert abs(gan - gan_r) < 0.05 + 0.05 * abs(gan_r)
     assert abs(feat - feat_r) < 0.05 * abs(feat_r) + 0.02
     assert abs(vl - vl_r) < 0.05 * abs(vl_r) + 0.01
+
+
+def test_vgg_loss_gradient_with_fused_relu_backward():
+    """VGGLoss through the kernels: the ReLU backward of every Vgg19 convolution is fused into its consumers (data-gradient epilogue of the
+    next convolution, max-pool backward, L1 backward — hrv_conv_params.res_mode) instead of running as a pass of its own.  Loss and
+    d loss / d image vs torch autograd through the same network in fp32 on the CPU; bound = what torch's own bf16 autocast costs."""
+    import networks
+    from hrviton_b200 import autograd_g
+    os.environ["HRV_VGG_RANDOM_INIT"] = "1"
+    torch.manual_seed(3)
+    vgg = networks.Vgg19().eval()
+    n, h, w = 2, 128, 96
+    x = (synth.uniform((n, 3, h, w), 5, "vggx")).requires_grad_(True)
+    y = synth.uniform((n, 3, h, w), 5, "vggy")
+    wts = [1.0 / 32, 1.0 / 16, 1.0 / 8, 1.0 / 4, 1.0]
+
+    def ref_loss(xx, autocast):
+        with torch.autocast("cpu", dtype=torch.bfloat16, enabled=autocast):
+            fx, fy = vgg(xx), vgg(y)
+            return sum(wt * torch.nn.functional.l1_loss(a.float(), b.float().detach()) for wt, a, b in zip(wts, fx, fy))
+
+    l_ref = ref_loss(x, False)
+    (g_ref,) = torch.autograd.grad(l_ref, x)
+    l_ac = ref_loss(x, True)
+    (g_ac,) = torch.autograd.grad(l_ac, x)
+    vg = networks.Vgg19().eval()
+    vg.load_state_dict(vgg.state_dict())
+    vg = vg.cuda()
+    xd = x.detach().cuda().requires_grad_(True)
+    loss = autograd_g.vgg_loss(vg, wts, xd, y.cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    g = xd.grad.cpu()
+    rel = float((g - g_ref).norm() / g_ref.norm())
+    rel_ac = float((g_ac - g_ref).norm() / g_ref.norm())
+    print("VGGGRAD loss %.5f vs %.5f (autocast %.5f) | d/dx rel L2 %.3e (torch bf16 autocast %.3e)" % (float(loss), float(l_ref), float(l_ac), rel, rel_ac))
+    assert abs(float(loss) - float(l_ref)) <= 1.25 * abs(float(l_ac) - float(l_ref)) + 2e-3 * abs(float(l_ref))
+    assert rel <= 1.25 * rel_ac + 1e-2

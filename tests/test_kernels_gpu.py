@@ -500,3 +500,18 @@ def test_onehot_u8():
     got = ops.onehot_u8(lab.to(DEV), 13).cpu()
     want = torch.zeros(3, 13, 37, 29).scatter_(1, lab.long(), 1.0)
     assert torch.equal(got, want)
+
+
+def test_conv_wgrad_is_bit_reproducible():
+    """Split-K partial tiles go to private workspace slabs and are summed in a fixed order (round 1 used fp32 atomics): two runs on the
+    same data give bit-identical dW, also for a layer whose element count is not a multiple of 4 (scalar reduction path)."""
+    for cin, cout, k, h, w in [(128, 160, 3, 192, 144), (13, 13, 3, 96, 80), (64, 128, 1, 256, 192)]:
+        x = Act(torch.randn(2, h, w, ops.round_up(cin, 8), device=DEV).to(torch.bfloat16), c=cin)
+        dy = Act(torch.randn(2, h, w, ops.round_up(cout, 8), device=DEV).to(torch.bfloat16), c=cout)
+        a = ops.conv2d_wgrad(x, dy, k, k, k // 2).clone()
+        for _ in range(3):
+            b = ops.conv2d_wgrad(x, dy, k, k, k // 2)
+            assert torch.equal(a, b), (cin, cout, k)
+        ref = torch.nn.grad.conv2d_weight(x.buf[..., :cin].permute(0, 3, 1, 2).float(), (cout, cin, k, k),
+                                          dy.buf[..., :cout].permute(0, 3, 1, 2).float(), padding=k // 2)
+        assert rel_err(a, ref) < 2e-3
