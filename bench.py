@@ -12,6 +12,7 @@ Prints ONE JSON line on rank 0.  Workloads (config.workload):
   train_stage1  one full train_condition.py step (tocg fwd+bwd with train-mode BatchNorm, stage-1 D, L1+VGG+TV+CE+LSGAN, Adam x2),
                 1024x768 per-GPU batch 4 (BASELINE.json configs[1])
   gen_fwd       SPADEGenerator inference forward, 1024x768, per-GPU batch 8 (BASELINE.json configs[2])
+  pipeline      end-to-end test_generator.py inference (tocg -> glue -> SPADE G), 1024x768, per-GPU batch 16 (BASELINE.json configs[4])
 """
 import argparse
 import json
@@ -409,7 +410,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch_gpu"])
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: 8 for train_stage2 and gen_fwd, 4 for train_stage1)")
-    ap.add_argument("--workload", default="train_stage2", choices=["train_stage2", "train_stage1", "gen_fwd"])
+    ap.add_argument("--workload", default="train_stage2", choices=["train_stage2", "train_stage1", "gen_fwd", "pipeline"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="train_stage2: launch eagerly instead of replaying a CUDA graph")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
@@ -442,7 +443,8 @@ def main():
     K = args.steps
     train = args.workload in ("train_stage2", "train_stage1")
     stage1 = args.workload == "train_stage1"
-    B = args.batch or (4 if stage1 else 8)
+    pipe = args.workload == "pipeline"
+    B = args.batch or (4 if stage1 else (16 if pipe else 8))
     if args.scaling == "strong":
         if B % world:
             raise SystemExit("--scaling strong: global batch %d is not divisible by %d ranks" % (B, world))
@@ -547,6 +549,37 @@ def main():
                 out = trainer.step(feeder.consume(batch_d), H, W)
             lk = ("loss_g", "loss_d") if stage1 else ("loss_gen", "loss_dis")
             loss_h.copy_(torch.stack([out[lk[0]].float(), out[lk[1]].float()]), non_blocking=True)
+    elif pipe:
+        # BASELINE.json configs[4]: the end-to-end test_generator.py pipeline (tocg -> parse post-processing -> hi-res warp with occlusion
+        # handling -> SPADEGenerator), 1024x768, batch 16, inference
+        import networks
+        from hrviton_b200 import pipeline, train_step
+        topt = types.SimpleNamespace(warp_feature="T1", out_layer="relu", cuda=True)
+        torch.manual_seed(0)
+        tocg = networks.ConditionGenerator(topt, 4, 16, 13, ngf=96, norm_layer=torch.nn.BatchNorm2d)
+        with torch.no_grad():
+            for mod in tocg.modules():
+                if isinstance(mod, torch.nn.BatchNorm2d):
+                    mod.running_mean.normal_(0, 0.1)
+                    mod.running_var.uniform_(0.5, 1.5)
+        tocg = tocg.to(dev).eval()
+        g = build_generator(dev)
+        batch_cpu = train_step.synthetic_batch(B, H, W, "cpu", seed=100 + rank)
+        batch_d = {k: v.to(dev) for k, v in batch_cpu.items()}
+        feeder = train_step.BatchFeeder(batch_cpu, dev)
+        del batch_cpu
+        out_h = torch.empty((B, 3, H, W), dtype=torch.float32).pin_memory()
+        h2d_bytes = feeder.bytes_per_step
+        d2h_bytes = int(out_h.numel() * 4)
+
+        def step_resident():
+            return pipeline.tryon_forward(tocg, g, batch_d, occlusion=True)[0]
+
+        feeder.prefetch()
+
+        def step_e2e():
+            out = pipeline.tryon_forward(tocg, g, feeder.consume(batch_d), occlusion=True)[0]
+            out_h.copy_(out, non_blocking=True)
     else:
         g = build_generator(dev)
         x_h, seg_h = synth_batch(B, "cpu", 100 + rank)
@@ -655,7 +688,8 @@ def main():
                 "data": "synthetic",
                 "config": {"workload": ("train_stage1: full train_condition.py step (tocg fwd+bwd with train-mode BatchNorm, 3 stage-1 D passes fwd+bwd, VGG loss x5 fwd+dgrad, L1/TV/CE/LSGAN, Adam x2; README flags --Ddownx2 --Ddropout --lasttvonly --interflowloss --occlusion), 1024x768, bf16 activations / fp32 accumulate" if (train and stage1) else
                                         "train_stage2: full train_generator.py step (tocg fwd, G fwd+bwd, D fwd+bwd x2, 2nd G fwd, VGG loss fwd+dgrad, Adam x2), 1024x768, bf16 activations / fp32 accumulate; convs (fwd/dgrad/wgrad), norms, modulation, activations, pooling, weight packing, parse-map glue, VGG L1 on this repo's kernels; hi-res grid_sample, hinge/feature-matching reductions, spectral-norm power iteration, Adam = torch"
-                                        if train else "gen_fwd: SPADEGenerator inference forward, 1024x768, bf16 activations, fp32 accumulate"),
+                                        if train else ("pipeline: end-to-end test_generator.py inference (tocg 256x192 -> parse post-processing -> hi-res cloth warp with occlusion handling -> SPADEGenerator), 1024x768, bf16 activations / fp32 accumulate"
+                                                       if pipe else "gen_fwd: SPADEGenerator inference forward, 1024x768, bf16 activations, fp32 accumulate")),
                            "launch": (("cuda-graph replay of the whole step" + (" (NCCL bucket all-reduces captured in the graph)" if world > 1 else "")) if (train and use_graph) else "eager"),
                            "feeding": "e2e: pinned host batch -> device on a copy stream, double-buffered (overlaps the previous step); one-hot parse maps shipped as uint8 labels and expanded by hrv_onehot_u8" if train else "e2e: pinned host -> device on the compute stream", "per_gpu_batch": B, "global_batch": B * world, "parallelism": "dp%d" % world,
                            "l2": "activations per step (>10 GB) exceed the 126 MB L2; no explicit flush",
@@ -663,7 +697,7 @@ def main():
                 "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": ms_e2e / K,
                         "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernel_breakdown": breakdown,
-                "model_tflops": (None if stage1 else (8800.0 if train else GEN_GFLOP_PER_IMG) * value / 1e3)}
+                "model_tflops": (None if stage1 else (8800.0 if train else (GEN_GFLOP_PER_IMG + 91.75 if pipe else GEN_GFLOP_PER_IMG)) * value / 1e3)}
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
         print(json.dumps(line))

@@ -63,6 +63,7 @@ struct alignas(64) ConvArgs {
   __nv_bfloat16* gamma_out;
   int gamma_pitch;
   int pairs, tiles_m, store_c;  // pixel-N variant: 256-pixel tiles (pairs of 128-pixel boxes), channels written per pixel
+  int epi_tab;                  // CTA-pair kernel, SPADE: per-warpgroup constant tables in shared memory
   unsigned long long* stats;    // debug (tools/conv_stall_probe.py): per-CTA cycle counters of the warp roles, or nullptr
 };
 
@@ -74,6 +75,316 @@ __device__ __forceinline__ void mbar_wait_acct(uint32_t bar, uint32_t parity, bo
   const long long t0 = clock64();  // try_wait itself may block for a hardware-defined time: time the whole wait
   mbar_wait(bar, parity);
   acc += (unsigned long long)(clock64() - t0);
+}
+
+// Activation as a compile-time choice: with a run-time `act` every element of an epilogue chunk carried its own uniform-branch ladder,
+// which serialised the eight elements of a thread (no ILP: ~500 dependent cycles per chunk in the SASS of the round-2 pair kernel).
+template <int ACT>
+__device__ __forceinline__ float act_t(float v) {
+  if (ACT == 1) return fmaxf(v, 0.f);
+  if (ACT == 2) return v > 0.f ? v : 0.2f * v;
+  if (ACT == 3) return tanhf(v);
+  return v;
+}
+// Activation of a chunk's eight values with ONE branch ladder per chunk (not one per element): the arithmetic above it stays
+// straight-line code, so the eight elements overlap instead of running one after the other.
+__device__ __forceinline__ void apply_act8(float (&f)[8], int act) {
+  if (act == 2) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = f[i] > 0.f ? f[i] : 0.2f * f[i];
+  } else if (act == 1) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
+  } else if (act == 3) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = tanhf(f[i]);
+  }
+}
+
+// One tile of the output as seen by an epilogue thread: TMEM lane r = pixel (x, y) of image n.
+struct EpiTile {
+  int x, y, n;
+  bool valid;
+  long long pix;
+  int n_base;       // first GEMM column of the tile's N tile
+  uint32_t taddr;   // TMEM address of this warp's lane quarter of the accumulator
+};
+constexpr int kMaxChunks = (256 / 16 + kEpiC - 1) / kEpiC;  // BN <= 256: at most 6 chunks of 16 columns per warpgroup
+
+// LINEAR epilogue of one tile (accumulator complete): out = act(acc*scale + shift (+ res | * act'(res))) for this warpgroup's chunks.
+__device__ __forceinline__ void epi_linear(const ConvArgs& a, const EpiTile& t, int wg, int nwg = kEpiC) {
+  const bool valid = t.valid;
+  const long long pix = t.pix;
+  const int n_base = t.n_base, n = t.n, y = t.y, x = t.x;
+  const uint32_t taddr = t.taddr;
+  const int store_c = (a.out_dtype == 0 && a.out_layout == 0) ? ((a.out_c + 7) & ~7) : a.out_c;
+  for (int col = wg * 16; col < a.BN; col += 16 * nwg) {
+    uint32_t v[16];
+    __syncwarp();
+    tmem_ld16(taddr + col, v);
+    tmem_wait_ld();
+    const int j0 = n_base + col;
+    if (!valid || j0 >= store_c) continue;
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      const int jg = j0 + g * 8;
+      if (jg >= store_c) break;
+      float f[8];
+      if (jg + 8 <= a.n_gemm) {  // vector path (scale/shift arrays are 16-byte aligned torch allocations)
+        float sc[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f}, sh[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (a.scale) {
+          *reinterpret_cast<float4*>(sc) = __ldg(reinterpret_cast<const float4*>(a.scale + jg));
+          *reinterpret_cast<float4*>(sc + 4) = __ldg(reinterpret_cast<const float4*>(a.scale + jg) + 1);
+        }
+        if (a.shift) {
+          *reinterpret_cast<float4*>(sh) = __ldg(reinterpret_cast<const float4*>(a.shift + jg));
+          *reinterpret_cast<float4*>(sh + 4) = __ldg(reinterpret_cast<const float4*>(a.shift + jg) + 1);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = fmaf(__uint_as_float(v[g * 8 + i]), sc[i], sh[i]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int j = jg + i;
+          const bool in = j < a.n_gemm;
+          const float sc = in ? (a.scale ? __ldg(a.scale + j) : 1.f) : 0.f;
+          const float sh = (in && a.shift) ? __ldg(a.shift + j) : 0.f;
+          f[i] = fmaf(__uint_as_float(v[g * 8 + i]), sc, sh);
+        }
+      }
+      if (a.res) {
+        if (a.res_dtype == 0) {
+          const uint4 rv = __ldg(reinterpret_cast<const uint4*>(
+              reinterpret_cast<const __nv_bfloat16*>(a.res) + pix * a.res_pitch + jg));
+          const float rf[8] = {bf16_lo(rv.x), bf16_hi(rv.x), bf16_lo(rv.y), bf16_hi(rv.y), bf16_lo(rv.z), bf16_hi(rv.z), bf16_lo(rv.w), bf16_hi(rv.w)};
+          if (a.res_mode == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] += rf[i];
+          } else {  // activation backward of the layer below, fused: multiply by act'(its saved output)
+            const float slope = a.res_mode == 1 ? 0.f : 0.2f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = rf[i] > 0.f ? f[i] : f[i] * slope;
+          }
+        } else {
+          const float* rp = reinterpret_cast<const float*>(a.res) + pix * a.res_pitch + jg;
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (jg + i < a.out_c) f[i] += __ldg(rp + i);
+        }
+      }
+      apply_act8(f, a.act);
+      if (a.out_dtype == 0) {
+        uint4 o;
+        o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]);
+        o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
+        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) + pix * a.out_pitch + jg) = o;
+      } else if (a.out_layout == 0) {
+        float* op = reinterpret_cast<float*>(a.out) + pix * a.out_pitch + jg;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (jg + i < a.out_c) op[i] = f[i];
+      } else {  // fp32 NCHW
+        float* op = reinterpret_cast<float*>(a.out);
+        const long long hw = (long long)a.Hout * a.Wout;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (jg + i < a.out_c) op[((long long)n * a.out_c + jg + i) * hw + (long long)y * a.Wout + x] = f[i];
+      }
+    }
+  }
+}
+
+// SPADE epilogue, part 1 (BEFORE waiting for the accumulator): issue the x loads of every chunk this warp owns and the noise load.
+// They do not depend on the MMAs, so their DRAM/L2 latency overlaps the mainloop instead of sitting on the epilogue's critical
+// path (the ncu source view of round 1 showed the epilogue warps stalled on the first use of x; profiles/r2_conv_stall_*.txt).
+__device__ __forceinline__ void epi_spade_prefetch(const ConvArgs& a, const EpiTile& t, int wg, uint4 (&xv)[kMaxChunks], float& nz_out) {
+  const bool valid = t.valid;
+  const long long pix = t.pix;
+  const int n_base = t.n_base, n = t.n, y = t.y, x = t.x;
+  const int sh0 = a.x0_shift;
+  const long long pix0 = ((long long)n * (a.Hout >> sh0) + (y >> sh0)) * (a.Wout >> sh0) + (x >> sh0);
+#pragma unroll
+  for (int k = 0; k < kMaxChunks; ++k) {
+    const int col = wg * 16 + k * 16 * kEpiC;
+    const int c0 = (n_base + col) >> 1;
+    xv[k] = make_uint4(0, 0, 0, 0);
+    if (col < a.BN && valid && c0 < a.C_mod) {
+      const __nv_bfloat16* xp = (c0 < a.x0_c) ? (a.x0 + pix0 * a.x0_pitch + c0)
+                                               : (a.x1 + pix * a.x1_pitch + (c0 - a.x0_c));
+      xv[k] = __ldg(reinterpret_cast<const uint4*>(xp));
+    }
+  }
+  nz_out = (valid && a.noise) ? __ldg(a.noise + pix) : 0.f;
+}
+
+// SPADE epilogue, part 2 (accumulator complete): 16 GEMM columns = 8 channels of (gamma, beta);
+// out = act(((x + noise*ns) - mean) * rstd * (1 + gamma) + beta), gamma optionally stored for the backward pass.
+__device__ __forceinline__ void epi_spade_finish(const ConvArgs& a, const EpiTile& t, int wg, const uint4 (&xv)[kMaxChunks], float nz) {
+  const bool valid = t.valid;
+  const long long pix = t.pix;
+  const int n_base = t.n_base, n = t.n;
+  const uint32_t taddr = t.taddr;
+#pragma unroll
+  for (int k = 0; k < kMaxChunks; ++k) {
+    const int col = wg * 16 + k * 16 * kEpiC;
+    if (col >= a.BN) break;
+    const int c0 = (n_base + col) >> 1;
+    const bool live = valid && c0 < a.C_mod;
+    // per-channel constants: warp-uniform addresses, L1-resident after the first tile of an image
+    float mu[8], rs[8], nsv[8], sh[16];
+    if (live) {
+      const float4* mp = reinterpret_cast<const float4*>(a.mean + (long long)n * a.C_mod + c0);
+      const float4* rp = reinterpret_cast<const float4*>(a.rstd + (long long)n * a.C_mod + c0);
+      *reinterpret_cast<float4*>(mu) = __ldg(mp);
+      *reinterpret_cast<float4*>(mu + 4) = __ldg(mp + 1);
+      *reinterpret_cast<float4*>(rs) = __ldg(rp);
+      *reinterpret_cast<float4*>(rs + 4) = __ldg(rp + 1);
+      if (a.noise_scale) {
+        const float4* np_ = reinterpret_cast<const float4*>(a.noise_scale + c0);
+        *reinterpret_cast<float4*>(nsv) = __ldg(np_);
+        *reinterpret_cast<float4*>(nsv + 4) = __ldg(np_ + 1);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) nsv[i] = 0.f;
+      }
+      if (a.shift) {
+        const float4* sp = reinterpret_cast<const float4*>(a.shift + 2 * c0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(sh + 4 * i) = __ldg(sp + i);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) sh[i] = 0.f;
+      }
+    }
+    uint32_t v[16];
+    __syncwarp();
+    tmem_ld16(taddr + col, v);
+    tmem_wait_ld();
+    if (!live) continue;
+    const uint4 xk = xv[k];
+    const float xs[8] = {bf16_lo(xk.x), bf16_hi(xk.x), bf16_lo(xk.y), bf16_hi(xk.y),
+                         bf16_lo(xk.z), bf16_hi(xk.z), bf16_lo(xk.w), bf16_hi(xk.w)};
+    float o[8], gmv[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float xval = fmaf(nz, nsv[i], xs[i]);
+      const float gm = __uint_as_float(v[2 * i]) + sh[2 * i];
+      const float bt = __uint_as_float(v[2 * i + 1]) + sh[2 * i + 1];
+      const float xn = (xval - mu[i]) * rs[i];
+      gmv[i] = gm;
+      o[i] = fmaf(xn, 1.f + gm, bt);
+    }
+    apply_act8(o, a.act);
+    if (a.gamma_out) {  // training: keep gamma for the backward pass (saves re-running this GEMM)
+      uint4 gv;
+      gv.x = pack_bf16(gmv[0], gmv[1]); gv.y = pack_bf16(gmv[2], gmv[3]);
+      gv.z = pack_bf16(gmv[4], gmv[5]); gv.w = pack_bf16(gmv[6], gmv[7]);
+      *reinterpret_cast<uint4*>(a.gamma_out + pix * a.gamma_pitch + c0) = gv;
+    }
+    uint4 ov;
+    ov.x = pack_bf16(o[0], o[1]); ov.y = pack_bf16(o[2], o[3]);
+    ov.z = pack_bf16(o[4], o[5]); ov.w = pack_bf16(o[6], o[7]);
+    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) + pix * a.out_pitch + c0) = ov;
+  }
+}
+
+// SPADE epilogue of a WHOLE tile by ONE warpgroup (CTA-pair kernel: the tile in TMEM accumulator w is drained by warpgroup w).
+// The per-chunk work is a chain of dependent latencies (tcgen05.ld -> constants -> arithmetic -> store) that leaves the issue slots
+// three quarters idle, and a warp walks its chunks one after the other: with all warpgroups on the SAME tile the tile period equals
+// that latency (about 10,000 cycles, tools/conv_stall_probe.py) however the stores are done.  With each warpgroup on its OWN tile three
+// tiles drain concurrently — one per TMEM accumulator (warpgroup w owns accumulator w; two of them when the tile is too wide for three
+// accumulators) — and the period drops accordingly.
+// x runs four chunks ahead of its use (the first four loads go out before the wait for the accumulator).
+// Per-warpgroup table of the current image's SPADE constants in shared memory, rows {mean, rstd, noise_scale, gamma bias, beta bias} of
+// C_mod floats: ten global loads per chunk (an L2 round trip on the critical path of every chunk) become broadcast shared-memory reads.
+constexpr int kTabMaxC = 288;
+constexpr uint32_t kTabBytes = ((5u * kTabMaxC * 4u) + 127u) & ~127u;
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void lds8(uint32_t addr, float (&f)[8]) {
+  const uint4 p = ld_shared_v4(addr), q = ld_shared_v4(addr + 16u);
+  f[0] = __uint_as_float(p.x); f[1] = __uint_as_float(p.y); f[2] = __uint_as_float(p.z); f[3] = __uint_as_float(p.w);
+  f[4] = __uint_as_float(q.x); f[5] = __uint_as_float(q.y); f[6] = __uint_as_float(q.z); f[7] = __uint_as_float(q.w);
+}
+__device__ __forceinline__ uint4 epi_spade_x(const ConvArgs& a, const EpiTile& t, int col, long long pix0) {
+  const int c0 = (t.n_base + col) >> 1;
+  if (col < a.BN && t.valid && c0 < a.C_mod) {
+    const __nv_bfloat16* xp = (c0 < a.x0_c) ? (a.x0 + pix0 * a.x0_pitch + c0) : (a.x1 + t.pix * a.x1_pitch + (c0 - a.x0_c));
+    return __ldg(reinterpret_cast<const uint4*>(xp));
+  }
+  return make_uint4(0, 0, 0, 0);
+}
+__device__ __forceinline__ void epi_spade_chunk(const ConvArgs& a, const EpiTile& t, int col, const uint4& xk, float nz, uint32_t tab) {
+  const int c0 = (t.n_base + col) >> 1;
+  const bool live = t.valid && c0 < a.C_mod;
+  float mu[8], rs[8], nsv[8], sh[16];
+  if (live && tab) {
+    float bg[8], bb[8];
+    const uint32_t cp = (uint32_t)a.C_mod * 4u, tb = tab + (uint32_t)c0 * 4u;
+    lds8(tb, mu); lds8(tb + cp, rs); lds8(tb + 2u * cp, nsv); lds8(tb + 3u * cp, bg); lds8(tb + 4u * cp, bb);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { sh[2 * i] = bg[i]; sh[2 * i + 1] = bb[i]; }
+  } else if (live) {
+    const float4* mp = reinterpret_cast<const float4*>(a.mean + (long long)t.n * a.C_mod + c0);
+    const float4* rp = reinterpret_cast<const float4*>(a.rstd + (long long)t.n * a.C_mod + c0);
+    *reinterpret_cast<float4*>(mu) = __ldg(mp);
+    *reinterpret_cast<float4*>(mu + 4) = __ldg(mp + 1);
+    *reinterpret_cast<float4*>(rs) = __ldg(rp);
+    *reinterpret_cast<float4*>(rs + 4) = __ldg(rp + 1);
+    if (a.noise_scale) {
+      const float4* np_ = reinterpret_cast<const float4*>(a.noise_scale + c0);
+      *reinterpret_cast<float4*>(nsv) = __ldg(np_);
+      *reinterpret_cast<float4*>(nsv + 4) = __ldg(np_ + 1);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) nsv[i] = 0.f;
+    }
+    if (a.shift) {
+      const float4* sp = reinterpret_cast<const float4*>(a.shift + 2 * c0);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(sh + 4 * i) = __ldg(sp + i);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) sh[i] = 0.f;
+    }
+  }
+  uint32_t v[16];
+  __syncwarp();
+  tmem_ld16(t.taddr + col, v);
+  tmem_wait_ld();
+  if (!live) return;
+  const float xs[8] = {bf16_lo(xk.x), bf16_hi(xk.x), bf16_lo(xk.y), bf16_hi(xk.y), bf16_lo(xk.z), bf16_hi(xk.z), bf16_lo(xk.w), bf16_hi(xk.w)};
+  float o[8], gmv[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float xval = fmaf(nz, nsv[i], xs[i]);
+    const float gm = __uint_as_float(v[2 * i]) + sh[2 * i];
+    const float bt = __uint_as_float(v[2 * i + 1]) + sh[2 * i + 1];
+    const float xn = (xval - mu[i]) * rs[i];
+    gmv[i] = gm;
+    o[i] = fmaf(xn, 1.f + gm, bt);
+  }
+  apply_act8(o, a.act);
+  if (a.gamma_out)
+    *reinterpret_cast<uint4*>(a.gamma_out + t.pix * a.gamma_pitch + c0) =
+        make_uint4(pack_bf16(gmv[0], gmv[1]), pack_bf16(gmv[2], gmv[3]), pack_bf16(gmv[4], gmv[5]), pack_bf16(gmv[6], gmv[7]));
+  *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) + t.pix * a.out_pitch + c0) =
+      make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+}
+
+// the whole-tile loop (accumulator complete; xv holds the x of chunks 0..3)
+__device__ __forceinline__ void epi_spade_tile(const ConvArgs& a, const EpiTile& t, long long pix0, float nz, uint4 (&xv)[4], uint32_t tab) {
+  const int nchunks = a.BN >> 4;
+  for (int k0 = 0; k0 < nchunks; k0 += 4) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (k0 + j < nchunks) epi_spade_chunk(a, t, (k0 + j) * 16, xv[j], nz, tab);
+      xv[j] = epi_spade_x(a, t, (k0 + 4 + j) * 16, pix0);  // refill: the load has three chunks of work to hide behind
+    }
+  }
 }
 
 template <int BK>
@@ -124,7 +435,7 @@ __global__ void __launch_bounds__(kThreadsC, 1) conv_igemm_kernel(const __grid_c
     }
     for (int i = 0; i < a.nacc; ++i) {
       mbar_init(bar_tfull(i), 1);
-      mbar_init(bar_tempty(i), 128 * kEpiC);
+      mbar_init(bar_tempty(i), 4 * kEpiC);  // one arrival per epilogue warp
     }
     fence_mbar_init();
   } else if (warp == 2) {
@@ -143,55 +454,32 @@ __global__ void __launch_bounds__(kThreadsC, 1) conv_igemm_kernel(const __grid_c
     // ===================================================== TMA producer (whole warp, warp-uniform; one elected lane issues)
     // All ring cursors (stage index, phase bit, smem address) advance incrementally: no divisions in the hot loops.
     const int taps = a.KH * a.KW;
+    (void)taps;
     if (a.halo) {
-      // halo ring cursor (runs ahead of the weight ring by up to S chunks, possibly into later tiles)
+      // halo (A) producer: runs ahead of the MMAs by up to S channel chunks, possibly into later tiles.  The weights have their own
+      // producer (warp 3): coupling the two in one loop made the weight loads of chunk k wait until the MMAs had released the halo
+      // stage of chunk k-1 (tools/conv_stall_probe.py: producer 59% blocked on a free halo stage while the MMA warp starved on weights)
       int as = 0, akc = 0, atile = blockIdx.x;
-      uint32_t aph = 0, a_addr = stage0, a_issued = 0, a_fed = 0;
-      int ax0 = 0, ay0 = 0, an0 = 0;
-      bool a_decode = true;
-      const uint32_t my_tiles = (uint32_t)((total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1);
-      const uint32_t my_chunks = my_tiles * (uint32_t)a.chunks;
-      int bs = 0;
-      uint32_t bph = 0, b_addr = bstage0;
-      const uint32_t b_tx = (uint32_t)a.tpb * b_bytes;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int nt = tile % a.tiles_n;
-        for (int kc = 0; kc < a.chunks; ++kc, ++a_fed) {
-          uint32_t want = a_fed + (uint32_t)S;
-          if (want > my_chunks) want = my_chunks;
-          while (a_issued < want) {
-            if (a_decode) {
-              int mta = atile / a.tiles_n;
-              const int txa = mta % a.tiles_x;
-              mta /= a.tiles_x;
-              const int tya = mta % a.tiles_y;
-              an0 = mta / a.tiles_y;
-              ax0 = (txa << a.tw_log) - a.off_x;
-              ay0 = (tya << a.th_log) - a.off_y;
-              a_decode = false;
-            }
-            mbar_wait_acct(bar_empty(as), aph ^ 1u, acct, w0);
-            if (elect_one()) {
-              mbar_arrive_expect_tx(bar_full(as), (uint32_t)a.a_stage_bytes_tx);
-              tma_load_4d(a_addr, &a.tmA, bar_full(as), akc * BK, ax0, ay0, an0);
-            }
-            __syncwarp();
-            ++a_issued;
-            a_addr += stage_bytes;
-            if (++as == S) { as = 0; aph ^= 1u; a_addr = stage0; }
-            if (++akc == a.chunks) { akc = 0; atile += gridDim.x; a_decode = true; }
+      uint32_t aph = 0, a_addr = stage0;
+      for (; atile < total_tiles;) {
+        int mta = atile / a.tiles_n;
+        const int txa = mta % a.tiles_x;
+        mta /= a.tiles_x;
+        const int tya = mta % a.tiles_y;
+        const int an0 = mta / a.tiles_y;
+        const int ax0 = (txa << a.tw_log) - a.off_x;
+        const int ay0 = (tya << a.th_log) - a.off_y;
+        for (akc = 0; akc < a.chunks; ++akc) {
+          mbar_wait_acct(bar_empty(as), aph ^ 1u, acct, w0);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(bar_full(as), (uint32_t)a.a_stage_bytes_tx);
+            tma_load_4d(a_addr, &a.tmA, bar_full(as), akc * BK, ax0, ay0, an0);
           }
-          for (int t0 = 0; t0 < taps; t0 += a.tpb) {
-            mbar_wait_acct(bar_bempty(bs), bph ^ 1u, acct, w1);
-            if (elect_one()) {
-              mbar_arrive_expect_tx(bar_bfull(bs), b_tx);
-              tma_load_3d(b_addr, &a.tmB, bar_bfull(bs), kc * BK, nt * a.BN, t0);
-            }
-            __syncwarp();
-            b_addr += (uint32_t)a.b_stage_bytes;
-            if (++bs == SB) { bs = 0; bph ^= 1u; b_addr = bstage0; }
-          }
+          __syncwarp();
+          a_addr += stage_bytes;
+          if (++as == S) { as = 0; aph ^= 1u; a_addr = stage0; }
         }
+        atile += gridDim.x;
       }
     } else {
       int st = 0;
@@ -225,7 +513,31 @@ __global__ void __launch_bounds__(kThreadsC, 1) conv_igemm_kernel(const __grid_c
         }
       }
     }
-    if (acct && lane == 0) { a.stats[blockIdx.x * 16 + 4] = w0; a.stats[blockIdx.x * 16 + 5] = w1; }
+    if (acct && lane == 0) a.stats[blockIdx.x * 16 + 4] = w0;
+  } else if (warp == 3) {
+    // ===================================================== weight (B) producer of the halo mainloop: `tpb` taps per TMA
+    if (a.halo) {
+      const int taps = a.KH * a.KW;
+      int bs = 0;
+      uint32_t bph = 0, b_addr = bstage0;
+      const uint32_t b_tx = (uint32_t)a.tpb * b_bytes;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile % a.tiles_n;
+        for (int kc = 0; kc < a.chunks; ++kc) {
+          for (int t0 = 0; t0 < taps; t0 += a.tpb) {
+            mbar_wait_acct(bar_bempty(bs), bph ^ 1u, acct, w1);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(bar_bfull(bs), b_tx);
+              tma_load_3d(b_addr, &a.tmB, bar_bfull(bs), kc * BK, nt * a.BN, t0);
+            }
+            __syncwarp();
+            b_addr += (uint32_t)a.b_stage_bytes;
+            if (++bs == SB) { bs = 0; bph ^= 1u; b_addr = bstage0; }
+          }
+        }
+      }
+      if (acct && lane == 0) a.stats[blockIdx.x * 16 + 5] = w1;
+    }
   } else if (warp == 1) {
     // ===================================================== MMA issuer (whole warp, warp-uniform; one elected lane issues)
     const uint32_t idesc = make_idesc_bf16(128, (uint32_t)a.BN);
@@ -330,177 +642,25 @@ __global__ void __launch_bounds__(kThreadsC, 1) conv_igemm_kernel(const __grid_c
       const bool valid = (x < a.Wout) && (y < a.Hout) && (n < a.Nimg);
       const long long pix = ((long long)n * a.Hout + y) * a.Wout + x;
 
-      const int n_base = nt * a.BN;
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)a.BN;
+      EpiTile et;
+      et.x = x; et.y = y; et.n = n; et.valid = valid; et.pix = pix; et.n_base = nt * a.BN;
+      et.taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)a.BN;
 
       if (a.epi == 0) {
         mbar_wait_acct(bar_tfull(acc), aph, acct, w0);
         tc_fence_after();
-        // ---------------- LINEAR
-        const int store_c = (a.out_dtype == 0 && a.out_layout == 0) ? ((a.out_c + 7) & ~7) : a.out_c;
-        for (int col = wg * 16; col < a.BN; col += 16 * kEpiC) {
-          uint32_t v[16];
-          __syncwarp();
-          tmem_ld16(taddr + col, v);
-          tmem_wait_ld();
-          const int j0 = n_base + col;
-          if (!valid || j0 >= store_c) continue;
-#pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            const int jg = j0 + g * 8;
-            if (jg >= store_c) break;
-            float f[8];
-            if (jg + 8 <= a.n_gemm) {  // vector path (scale/shift arrays are 16-byte aligned torch allocations)
-              float sc[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f}, sh[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-              if (a.scale) {
-                *reinterpret_cast<float4*>(sc) = __ldg(reinterpret_cast<const float4*>(a.scale + jg));
-                *reinterpret_cast<float4*>(sc + 4) = __ldg(reinterpret_cast<const float4*>(a.scale + jg) + 1);
-              }
-              if (a.shift) {
-                *reinterpret_cast<float4*>(sh) = __ldg(reinterpret_cast<const float4*>(a.shift + jg));
-                *reinterpret_cast<float4*>(sh + 4) = __ldg(reinterpret_cast<const float4*>(a.shift + jg) + 1);
-              }
-#pragma unroll
-              for (int i = 0; i < 8; ++i) f[i] = fmaf(__uint_as_float(v[g * 8 + i]), sc[i], sh[i]);
-            } else {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const int j = jg + i;
-                const bool in = j < a.n_gemm;
-                const float sc = in ? (a.scale ? __ldg(a.scale + j) : 1.f) : 0.f;
-                const float sh = (in && a.shift) ? __ldg(a.shift + j) : 0.f;
-                f[i] = fmaf(__uint_as_float(v[g * 8 + i]), sc, sh);
-              }
-            }
-            if (a.res) {
-              if (a.res_dtype == 0) {
-                const uint4 rv = __ldg(reinterpret_cast<const uint4*>(
-                    reinterpret_cast<const __nv_bfloat16*>(a.res) + pix * a.res_pitch + jg));
-                const float rf[8] = {bf16_lo(rv.x), bf16_hi(rv.x), bf16_lo(rv.y), bf16_hi(rv.y), bf16_lo(rv.z), bf16_hi(rv.z), bf16_lo(rv.w), bf16_hi(rv.w)};
-                if (a.res_mode == 0) {
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) f[i] += rf[i];
-                } else {  // activation backward of the layer below, fused: multiply by act'(its saved output)
-                  const float slope = a.res_mode == 1 ? 0.f : 0.2f;
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) f[i] = rf[i] > 0.f ? f[i] : f[i] * slope;
-                }
-              } else {
-                const float* rp = reinterpret_cast<const float*>(a.res) + pix * a.res_pitch + jg;
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                  if (jg + i < a.out_c) f[i] += __ldg(rp + i);
-              }
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) f[i] = apply_act(f[i], a.act);
-            if (a.out_dtype == 0) {
-              uint4 o;
-              o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]);
-              o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
-              *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) + pix * a.out_pitch + jg) = o;
-            } else if (a.out_layout == 0) {
-              float* op = reinterpret_cast<float*>(a.out) + pix * a.out_pitch + jg;
-#pragma unroll
-              for (int i = 0; i < 8; ++i)
-                if (jg + i < a.out_c) op[i] = f[i];
-            } else {  // fp32 NCHW
-              float* op = reinterpret_cast<float*>(a.out);
-              const long long hw = (long long)a.Hout * a.Wout;
-#pragma unroll
-              for (int i = 0; i < 8; ++i)
-                if (jg + i < a.out_c) op[((long long)n * a.out_c + jg + i) * hw + (long long)y * a.Wout + x] = f[i];
-            }
-          }
-        }
+        epi_linear(a, et, wg);
       } else {
-        // ---------------- SPADE: 16 GEMM columns = 8 channels of (gamma, beta)
-        // The x (and noise) loads do not depend on the accumulator: all of this warp's chunks issue them BEFORE waiting for the MMAs
-        // of the tile, so their DRAM/L2 latency overlaps the mainloop instead of sitting on the epilogue's critical path (the ncu
-        // source view of round 1 showed the epilogue warps stalled on the first use of x; profiles/r2_conv_stall_*.txt).
-        constexpr int kMaxChunks = (256 / 16 + kEpiC - 1) / kEpiC;  // BN <= 256: at most 6 chunks of 16 columns per warpgroup
-        const int sh0 = a.x0_shift;
-        const long long pix0 = ((long long)n * (a.Hout >> sh0) + (y >> sh0)) * (a.Wout >> sh0) + (x >> sh0);
         uint4 xv[kMaxChunks];
-#pragma unroll
-        for (int k = 0; k < kMaxChunks; ++k) {
-          const int col = wg * 16 + k * 16 * kEpiC;
-          const int c0 = (n_base + col) >> 1;
-          xv[k] = make_uint4(0, 0, 0, 0);
-          if (col < a.BN && valid && c0 < a.C_mod) {
-            const __nv_bfloat16* xp = (c0 < a.x0_c) ? (a.x0 + pix0 * a.x0_pitch + c0)
-                                                     : (a.x1 + pix * a.x1_pitch + (c0 - a.x0_c));
-            xv[k] = __ldg(reinterpret_cast<const uint4*>(xp));
-          }
-        }
-        const float nz = (valid && a.noise) ? __ldg(a.noise + pix) : 0.f;
+        float nz;
+        epi_spade_prefetch(a, et, wg, xv, nz);
         mbar_wait_acct(bar_tfull(acc), aph, acct, w0);
         tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < kMaxChunks; ++k) {
-          const int col = wg * 16 + k * 16 * kEpiC;
-          if (col >= a.BN) break;
-          const int c0 = (n_base + col) >> 1;
-          const bool live = valid && c0 < a.C_mod;
-          // per-channel constants: warp-uniform addresses, L1-resident after the first tile of an image
-          float mu[8], rs[8], nsv[8], sh[16];
-          if (live) {
-            const float4* mp = reinterpret_cast<const float4*>(a.mean + (long long)n * a.C_mod + c0);
-            const float4* rp = reinterpret_cast<const float4*>(a.rstd + (long long)n * a.C_mod + c0);
-            *reinterpret_cast<float4*>(mu) = __ldg(mp);
-            *reinterpret_cast<float4*>(mu + 4) = __ldg(mp + 1);
-            *reinterpret_cast<float4*>(rs) = __ldg(rp);
-            *reinterpret_cast<float4*>(rs + 4) = __ldg(rp + 1);
-            if (a.noise_scale) {
-              const float4* np_ = reinterpret_cast<const float4*>(a.noise_scale + c0);
-              *reinterpret_cast<float4*>(nsv) = __ldg(np_);
-              *reinterpret_cast<float4*>(nsv + 4) = __ldg(np_ + 1);
-            } else {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) nsv[i] = 0.f;
-            }
-            if (a.shift) {
-              const float4* sp = reinterpret_cast<const float4*>(a.shift + 2 * c0);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(sh + 4 * i) = __ldg(sp + i);
-            } else {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) sh[i] = 0.f;
-            }
-          }
-          uint32_t v[16];
-          __syncwarp();
-          tmem_ld16(taddr + col, v);
-          tmem_wait_ld();
-          if (!live) continue;
-          const uint4 xk = xv[k];
-          const float xs[8] = {bf16_lo(xk.x), bf16_hi(xk.x), bf16_lo(xk.y), bf16_hi(xk.y),
-                               bf16_lo(xk.z), bf16_hi(xk.z), bf16_lo(xk.w), bf16_hi(xk.w)};
-          float o[8], gmv[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float xval = fmaf(nz, nsv[i], xs[i]);
-            const float gm = __uint_as_float(v[2 * i]) + sh[2 * i];
-            const float bt = __uint_as_float(v[2 * i + 1]) + sh[2 * i + 1];
-            const float xn = (xval - mu[i]) * rs[i];
-            gmv[i] = gm;
-            o[i] = apply_act(fmaf(xn, 1.f + gm, bt), a.act);
-          }
-          if (a.gamma_out) {  // training: keep gamma for the backward pass (saves re-running this GEMM)
-            uint4 gv;
-            gv.x = pack_bf16(gmv[0], gmv[1]); gv.y = pack_bf16(gmv[2], gmv[3]);
-            gv.z = pack_bf16(gmv[4], gmv[5]); gv.w = pack_bf16(gmv[6], gmv[7]);
-            *reinterpret_cast<uint4*>(a.gamma_out + pix * a.gamma_pitch + c0) = gv;
-          }
-          uint4 ov;
-          ov.x = pack_bf16(o[0], o[1]); ov.y = pack_bf16(o[2], o[3]);
-          ov.z = pack_bf16(o[4], o[5]); ov.w = pack_bf16(o[6], o[7]);
-          *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) + pix * a.out_pitch + c0) = ov;
-        }
+        epi_spade_finish(a, et, wg, xv, nz);
       }
-      __syncwarp();
       tc_fence_before();
-      mbar_arrive(bar_tempty(acc));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty(acc));  // one arrival per warp (12 per tile instead of 384)
       if (++acc == NACC) { acc = 0; aph ^= 1u; }
     }
     if (acct && warp == 4 && lane == 0) {  // first epilogue warp: time stalled on the accumulator vs total
@@ -516,6 +676,254 @@ __global__ void __launch_bounds__(kThreadsC, 1) conv_igemm_kernel(const __grid_c
   }
 }
 
+// ------------------------------------------------------------------------------------------------ CTA-pair variant (cta_group::2)
+// The one-CTA kernel above is bound by SHARED-MEMORY bandwidth, not by the tensor pipe, whenever the GEMM's N is wide and K is
+// streamed: per 128-pixel tile of the 128 -> 160 SPADE GEMM the tensor core reads 72 x (4 KB of A + 5 KB of B) = 663 KB and TMA
+// writes 46 KB (halo) + 368 KB (weights) = 414 KB; 1077 KB at 128 B/clk = 8400 cycles against 5760 cycles of MMAs
+// (tools/conv_stall_probe.py: the MMA warp spends 75% of its life blocked on issue, 23% waiting for weights; tools/umma_rate_probe.cu:
+// the same MMAs run at 100% when nothing else touches shared memory).  A CTA PAIR issues ONE tcgen05.mma.cta_group::2 of M = 256:
+// each CTA brings its own 128 pixels (halo box) and only HALF of every weight stage, so per CTA the weight bytes through shared
+// memory halve (written: 184 KB, read: 72 x 2.5 KB) -> 705 KB per tile, under the MMA time.
+//   pair = thread-block cluster of 2 on one TPC; rank 0 = leader.  Work item = (pair of adjacent pixel tiles, N tile).
+//   TMA:  both CTAs load into their own shared memory and signal the LEADER's full barriers (cp.async.bulk.tensor ... .cta_group::2).
+//   MMA:  the leader's warp 1 issues for both; tcgen05.commit ... .multicast::cluster releases the ring stages / publishes the
+//         accumulator in BOTH CTAs.
+//   Epilogue: each CTA drains its own TMEM; all 2 x 384 epilogue threads arrive on the leader's accumulator-empty barrier.
+// Halo mainloop, BK = 64, both epilogues (shared with the one-CTA kernel).  HRV_CONV_PAIR=0 disables it.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsC, 1) conv_pair_kernel(const __grid_constant__ ConvArgs a) {
+  constexpr uint32_t ROW_BYTES = 128;  // BK = 64 bf16
+  constexpr uint32_t LAYOUT = 2u;      // SWIZZLE_128B
+  constexpr int BK = 64;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  auto bar_full = [&](int s) { return base + 8u * s; };            // leader: halo stage landed in BOTH CTAs
+  auto bar_empty = [&](int s) { return base + 256u + 8u * s; };    // local: this CTA's halo stage may be overwritten
+  auto bar_bfull = [&](int s) { return base + 512u + 8u * s; };    // leader: both halves of a weight stage landed
+  auto bar_bempty = [&](int s) { return base + 768u + 8u * s; };   // local
+  auto bar_tfull = [&](int i) { return base + 1024u + 8u * i; };   // local: accumulator i complete
+  auto bar_tempty = [&](int i) { return base + 1088u + 8u * i; };  // leader: accumulator i drained by both CTAs
+  const uint32_t tmem_slot = base + 1152u;
+  const uint32_t NACC = (uint32_t)a.nacc;
+  const uint32_t half_rows = (uint32_t)a.BN >> 1;
+  const uint32_t b_bytes = half_rows * ROW_BYTES;  // one tap of this CTA's half of the weight tile
+  const uint32_t stage_bytes = (uint32_t)a.a_stage_bytes;
+  const uint32_t tab0 = base + 2048u;  // kEpiC constant tables (SPADE with C_mod <= kTabMaxC), then the rings
+  const uint32_t stage0 = tab0 + (a.epi_tab ? ((uint32_t)kEpiC * kTabBytes + 1023u) & ~1023u : 0u);
+  const uint32_t bstage0 = stage0 + (uint32_t)a.stages * stage_bytes;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cid = (int)cluster_id_x(), ncl = (int)cluster_nctaid_x();
+  const int S = a.stages, SB = a.sb_stages;
+  const int taps = a.KH * a.KW;
+  const int tiles_m = a.tiles_x * a.tiles_y * a.tiles_img;
+  const int items = a.tiles_n * ((tiles_m + 1) >> 1);
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < (uint32_t)a.nacc * a.BN) tmem_cols <<= 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&a.tmA);
+    tma_prefetch_desc(&a.tmB);
+  } else if (warp == 1 && lane == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
+    for (int s = 0; s < SB; ++s) { mbar_init(bar_bfull(s), 1); mbar_init(bar_bempty(s), 1); }
+    for (int i = 0; i < a.nacc; ++i) { mbar_init(bar_tfull(i), 1); mbar_init(bar_tempty(i), 2 * 4); }  // one arrival per warp of the owning warpgroup in either CTA
+    fence_mbar_init();
+  } else if (warp == 2) {
+    tmem_alloc2(tmem_slot, tmem_cols);
+    tmem_relinquish2();
+  }
+  tc_fence_before();
+  cluster_sync_all();  // barriers of BOTH CTAs initialised before anyone signals the leader's
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+  const bool acct = a.stats != nullptr && leader;
+  unsigned long long w0 = 0, w1 = 0, w2 = 0;
+  const long long t_begin = acct ? clock64() : 0;
+
+  if (warp == 0) {
+    // ===================================================== halo (A) producer (both CTAs): own pixel tile of every pair; runs ahead of the
+    // MMAs by up to S channel chunks.  The transaction bytes of both CTAs are expected on the LEADER's full barrier.
+    int as = 0;
+    uint32_t aph = 0, a_addr = stage0;
+    for (int item = cid; item < items; item += ncl) {
+      int mta = 2 * (item / a.tiles_n) + (int)rank;  // may lie past the last tile (odd tile count): TMA zero-fills, the epilogue skips it
+      const int txa = mta % a.tiles_x;
+      mta /= a.tiles_x;
+      const int tya = mta % a.tiles_y;
+      const int an0 = mta / a.tiles_y;
+      const int ax0 = (txa << a.tw_log) - a.off_x;
+      const int ay0 = (tya << a.th_log) - a.off_y;
+      for (int akc = 0; akc < a.chunks; ++akc) {
+        mbar_wait_acct(bar_empty(as), aph ^ 1u, acct, w0);
+        if (elect_one()) {
+          if (leader) mbar_arrive_expect_tx(bar_full(as), 2u * (uint32_t)a.a_stage_bytes_tx);
+          tma_load_4d_2sm(a_addr, &a.tmA, bar_full(as), akc * BK, ax0, ay0, an0);
+        }
+        __syncwarp();
+        a_addr += stage_bytes;
+        if (++as == S) { as = 0; aph ^= 1u; a_addr = stage0; }
+      }
+    }
+    if (acct && lane == 0) a.stats[cid * 16 + 4] = w0;
+  } else if (warp == 3) {
+    // ===================================================== weight (B) producer (both CTAs): THIS CTA's half of every weight stage
+    int bs = 0;
+    uint32_t bph = 0, b_addr = bstage0;
+    const uint32_t b_tx = (uint32_t)a.tpb * b_bytes;
+    for (int item = cid; item < items; item += ncl) {
+      const int nt = item % a.tiles_n;
+      for (int kc = 0; kc < a.chunks; ++kc) {
+        for (int t0 = 0; t0 < taps; t0 += a.tpb) {
+          mbar_wait_acct(bar_bempty(bs), bph ^ 1u, acct, w1);
+          if (elect_one()) {
+            if (leader) mbar_arrive_expect_tx(bar_bfull(bs), 2u * b_tx);
+            tma_load_3d_2sm(b_addr, &a.tmB, bar_bfull(bs), kc * BK, nt * a.BN + (int)(rank * half_rows), t0);
+          }
+          __syncwarp();
+          b_addr += (uint32_t)a.b_stage_bytes;
+          if (++bs == SB) { bs = 0; bph ^= 1u; b_addr = bstage0; }
+        }
+      }
+    }
+    if (acct && lane == 0) a.stats[cid * 16 + 5] = w1;
+  } else if (warp == 1 && leader) {
+    // ===================================================== MMA issuer (leader only): M = 256 over the pair
+    const uint32_t idesc = make_idesc_bf16(256, (uint32_t)a.BN);
+    const uint64_t db_hi = make_smem_desc(0, 8 * ROW_BYTES, LAYOUT);
+    const uint64_t da_hi = make_smem_desc(0, (uint32_t)a.line_pitch * ROW_BYTES, LAYOUT);  // SBO = one output row of 8 px
+    const uint32_t row_wrap = (uint32_t)(a.line_pitch - a.KW) * ROW_BYTES;
+    uint32_t acc = 0, acc_ph = 0;
+    int as = 0, bs = 0;
+    uint32_t aph = 0, bph = 0, a_addr = stage0, b_addr = bstage0;
+    for (int item = cid; item < items; item += ncl) {
+      mbar_wait_acct(bar_tempty(acc), acc_ph ^ 1u, acct, w2);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * (uint32_t)a.BN;
+      uint32_t accumulate = 0;
+      for (int kc = 0; kc < a.chunks; ++kc) {
+        mbar_wait_acct(bar_full(as), aph, acct, w0);
+        uint32_t sa_tap = a_addr;
+        int kx = 0;
+        for (int t0 = 0; t0 < taps; t0 += a.tpb) {
+          mbar_wait_acct(bar_bfull(bs), bph, acct, w1);
+          tc_fence_after();
+          uint32_t sb_tap = b_addr;
+          for (int t = 0; t < a.tpb; ++t) {
+            const uint64_t da = da_hi | (uint64_t)((sa_tap & 0x3FFFFu) >> 4);
+            const uint64_t db = db_hi | (uint64_t)((sb_tap & 0x3FFFFu) >> 4);
+            if (elect_one()) {
+#pragma unroll
+              for (int kk = 0; kk < BK / 16; ++kk) umma_f16_2sm(d_tmem, da + 2u * kk, db + 2u * kk, idesc, (kk == 0) ? accumulate : 1u);
+            }
+            __syncwarp();
+            accumulate = 1;
+            sb_tap += b_bytes;
+            sa_tap += ROW_BYTES;
+            if (++kx == a.KW) { kx = 0; sa_tap += row_wrap; }
+          }
+          if (elect_one()) umma_commit_2sm(bar_bempty(bs));  // weight stage free in both CTAs
+          __syncwarp();
+          b_addr += (uint32_t)a.b_stage_bytes;
+          if (++bs == SB) { bs = 0; bph ^= 1u; b_addr = bstage0; }
+        }
+        if (elect_one()) umma_commit_2sm(bar_empty(as));  // halo stage free in both CTAs
+        __syncwarp();
+        a_addr += stage_bytes;
+        if (++as == S) { as = 0; aph ^= 1u; a_addr = stage0; }
+      }
+      if (elect_one()) umma_commit_2sm(bar_tfull(acc));  // accumulator complete -> both epilogues
+      __syncwarp();
+      if (++acc == NACC) { acc = 0; acc_ph ^= 1u; }
+    }
+    if (acct && lane == 0) {
+      unsigned long long* o = a.stats + cid * 16;
+      o[0] = (unsigned long long)(clock64() - t_begin); o[1] = w0; o[2] = w1; o[3] = w2;
+      o[8] = items > cid ? (unsigned long long)((items - 1 - cid) / ncl + 1) : 0ull;
+    }
+  } else if (warp >= 4) {
+    // ===================================================== epilogue (both CTAs, own TMEM)
+    const int q = warp & 3;
+    const int wg = (warp - 4) >> 2;
+    const int r = q * 32 + lane;
+    const int tw_mask = (1 << a.tw_log) - 1, th_mask = (1 << a.th_log) - 1;
+    uint32_t acc = 0, aph = 0;
+    const uint32_t tab = a.epi_tab ? tab0 + (uint32_t)wg * kTabBytes : 0u;
+    int tab_n = -1;  // image whose constants this warpgroup's table holds
+    for (int item = cid; item < items; item += ncl) {
+      if ((int)acc != wg) {  // the tile in accumulator `acc` belongs to warpgroup `acc` (NACC <= kEpiC): keep the ring cursor in step.
+        // One owner per accumulator also keeps every warpgroup within one phase of the barriers it waits on — an mbarrier parity wait
+        // is ambiguous for a waiter two phases ahead or behind, which a round-robin over tiles would allow when NACC != kEpiC.
+        if (++acc == NACC) { acc = 0; aph ^= 1u; }
+        continue;
+      }
+      const int nt = item % a.tiles_n;
+      int mt = 2 * (item / a.tiles_n) + (int)rank;
+      const int tx = mt % a.tiles_x;
+      mt /= a.tiles_x;
+      const int ty = mt % a.tiles_y;
+      const int ti = mt / a.tiles_y;
+      EpiTile et;
+      et.x = (tx << a.tw_log) + (r & tw_mask);
+      et.y = (ty << a.th_log) + ((r >> a.tw_log) & th_mask);
+      et.n = (ti << (7 - a.tw_log - a.th_log)) + (r >> (a.tw_log + a.th_log));
+      et.valid = (et.x < a.Wout) && (et.y < a.Hout) && (et.n < a.Nimg);
+      et.pix = ((long long)et.n * a.Hout + et.y) * a.Wout + et.x;
+      et.n_base = nt * a.BN;
+      et.taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)a.BN;
+      if (a.epi == 0) {
+        mbar_wait_acct(bar_tfull(acc), aph, acct, w0);
+        tc_fence_after();
+        epi_linear(a, et, 0, 1);
+      } else {
+        const int sh0 = a.x0_shift;
+        const long long pix0 = ((long long)et.n * (a.Hout >> sh0) + (et.y >> sh0)) * (a.Wout >> sh0) + (et.x >> sh0);
+        const float nz = (et.valid && a.noise) ? __ldg(a.noise + et.pix) : 0.f;
+        uint4 xv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) xv[j] = epi_spade_x(a, et, j * 16, pix0);
+        if (tab && ti != tab_n && ti < a.Nimg) {  // (halo tiles hold one image: ti is the image index)  new image: refill the table
+          named_bar_sync(1 + wg, 128);            // every warp of the warpgroup is past its reads of the old table
+          float* T = reinterpret_cast<float*>(smem_raw + (tab - raw));
+          for (int c = r; c < a.C_mod; c += 128) {
+            T[c] = __ldg(a.mean + (long long)ti * a.C_mod + c);
+            T[a.C_mod + c] = __ldg(a.rstd + (long long)ti * a.C_mod + c);
+            T[2 * a.C_mod + c] = a.noise_scale ? __ldg(a.noise_scale + c) : 0.f;
+            T[3 * a.C_mod + c] = a.shift ? __ldg(a.shift + 2 * c) : 0.f;
+            T[4 * a.C_mod + c] = a.shift ? __ldg(a.shift + 2 * c + 1) : 0.f;
+          }
+          named_bar_sync(1 + wg, 128);
+          tab_n = ti;
+        }
+        mbar_wait_acct(bar_tfull(acc), aph, acct, w0);
+        tc_fence_after();
+        epi_spade_tile(a, et, pix0, nz, xv, tab);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(bar_tempty(acc));  // ONE (possibly remote) arrival per warp: 24 per item instead of 768 — remote
+                                                           // mbarrier arrivals are DSMEM transactions and serialise at the leader
+      if (++acc == NACC) { acc = 0; aph ^= 1u; }
+    }
+    if (acct && warp == 4 && lane == 0) {
+      a.stats[cid * 16 + 6] = w0;
+      a.stats[cid * 16 + 7] = (unsigned long long)(clock64() - t_begin);
+
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // nobody leaves (or frees TMEM) while the peer may still signal / read this CTA
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, tmem_cols);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ pixel-N variant
 // tcgen05.mma (both operands in shared memory) costs ~153 cycles per K=16 instruction on B200 whatever M and N are
 // (tools/umma_rate_probe.cu, profiles/r1_umma_rate_probe.txt), so a convolution with few output channels wastes the tensor pipe
@@ -525,13 +933,6 @@ __global__ void __launch_bounds__(kThreadsC, 1) conv_igemm_kernel(const __grid_c
 // The epilogue thread owns one output channel (a TMEM lane): scale/shift/activation per thread, then a bf16 transpose through
 // shared memory so that every pixel's channels leave as contiguous 16-byte vectors (coalesced stores).
 // Tap-by-tap loading, BK = 64, LINEAR epilogue, bf16 NHWC output without residual; everything else stays on conv_igemm_kernel.
-template <int ACT>
-__device__ __forceinline__ float act_t(float v) {
-  if (ACT == 1) return fmaxf(v, 0.f);
-  if (ACT == 2) return v > 0.f ? v : 0.2f * v;
-  if (ACT == 3) return tanhf(v);
-  return v;
-}
 // One thread = one output channel: 64 pixels (4 x tcgen05.ld of 16 columns) -> act(acc*sc+sh) -> bf16 -> column `tp` of the
 // [64 px][pitch] staging tile.
 template <int ACT>
@@ -845,6 +1246,12 @@ extern "C" int hrv_conv2d_fwd(const hrv_conv_params* p, hrv_stream stream) {
   bool halo = out.h >= 12 && p->kh * p->kw > 1 && halo_shape && !pixn;
   if (force && force[0] == '0') halo = false;
   if (force && force[0] == '1') halo = true;
+  // CTA-pair kernel (cta_group::2, M = 256 over two SMs, each CTA holds half of every weight stage): wide-N 3x3 GEMMs whose one-CTA
+  // form is bound by shared-memory bandwidth.  Needs the halo mainloop, 64-channel K blocks and an even SM count.
+  const char* env_pair = getenv("HRV_CONV_PAIR");  // read per call (tests compare the two kernels on identical inputs)
+  const bool pair_shape = p->bk == 64 && p->bn >= 144 && p->bn <= 256 && (p->bn % 16) == 0 && out.h >= 12 && p->kh * p->kw > 1 && !pixn;
+  const bool pair = pair_shape && !(env_pair && env_pair[0] == '0') && !(force && force[0] == '0') && (sm_count() % 2) == 0;
+  if (pair) halo = true;
   const int TW = halo ? 8 : pick_pow2(out.w, 128);
   const int TH = halo ? 16 : pick_pow2(out.h, 128 / TW);
   const int TN = 128 / (TW * TH);
@@ -857,6 +1264,7 @@ extern "C" int hrv_conv2d_fwd(const hrv_conv_params* p, hrv_stream stream) {
   a.chunks = (in.c + p->bk - 1) / p->bk;
   a.BN = p->bn; a.n_gemm = p->n_gemm;
   a.nacc = 512 / p->bn > 8 ? 8 : 512 / p->bn;
+  if (pair && a.nacc > kEpiC) a.nacc = kEpiC;  // pair kernel: accumulator w is drained by epilogue warpgroup w
   a.epi = p->epi; a.act = p->act;
   a.scale = p->scale; a.shift = p->shift;
   a.out = out.ptr; a.out_pitch = out.pitch; a.out_dtype = out.dtype; a.out_layout = p->out_layout; a.out_c = out.c;
@@ -888,11 +1296,14 @@ extern "C" int hrv_conv2d_fwd(const hrv_conv_params* p, hrv_stream stream) {
     return set_error(HRV_EINVAL, "conv: unknown epilogue %d", p->epi);
   }
 
+  // per-warpgroup SPADE constant tables of the pair kernel
+  a.epi_tab = (pair && p->epi == HRV_EPI_SPADE && a.C_mod <= kTabMaxC && (a.C_mod % 8) == 0) ? 1 : 0;
+  const uint32_t tab_bytes = a.epi_tab ? (((uint32_t)kEpiC * kTabBytes + 1023u) & ~1023u) : 0u;
   // ---- pipeline geometry
   const int elem = 2;
   const int taps = p->kh * p->kw;
   const uint32_t row_bytes = p->bk * 2;
-  const uint32_t budget = 225u * 1024u - 3072u;  // 1 KB alignment slack + 2 KB control block
+  const uint32_t budget = 225u * 1024u - 3072u - tab_bytes;  // 1 KB alignment slack + 2 KB control block (+ constant tables)
   const int LP = TW + p->kw - 1, HRows = (TH + p->kh - 1) * LP;
   int tpb = 1;
   if (halo) {
@@ -910,13 +1321,14 @@ extern "C" int hrv_conv2d_fwd(const hrv_conv_params* p, hrv_stream stream) {
     if (env_sa) sa = atoi(env_sa);
     // taps per weight TMA: the largest divisor of the tap count whose stage is <= tpb_cap and still leaves >= 3 weight stages
     // (>= 2 as a last resort) next to the halo ring
+    const uint32_t b_rows = pair ? (uint32_t)p->bn / 2u : (uint32_t)p->bn;  // weight rows per tap in THIS CTA's shared memory
     for (int want = 3; want >= 2 && tpb == 1; --want)
       for (int d = taps; d >= 1; --d) {
-        const uint32_t bs = ((uint32_t)d * p->bn * row_bytes + 1023u) & ~1023u;
-        if (taps % d == 0 && (uint32_t)d * p->bn * row_bytes <= tpb_cap && (uint32_t)sa * a.a_stage_bytes + (uint32_t)want * bs <= budget) { tpb = d; break; }
+        const uint32_t bs = ((uint32_t)d * b_rows * row_bytes + 1023u) & ~1023u;
+        if (taps % d == 0 && (uint32_t)d * b_rows * row_bytes <= tpb_cap && (uint32_t)sa * a.a_stage_bytes + (uint32_t)want * bs <= budget) { tpb = d; break; }
       }
     a.tpb = tpb;
-    a.b_stage_bytes = (int)(((uint32_t)tpb * p->bn * row_bytes + 1023u) & ~1023u);
+    a.b_stage_bytes = (int)(((uint32_t)tpb * b_rows * row_bytes + 1023u) & ~1023u);
     while (sa > 2 && (uint32_t)sa * a.a_stage_bytes + 2u * a.b_stage_bytes > budget) --sa;
     int sb = (int)((budget - (uint32_t)sa * a.a_stage_bytes) / (uint32_t)a.b_stage_bytes);
     if (sb > kMaxStages) sb = kMaxStages;
@@ -945,7 +1357,7 @@ extern "C" int hrv_conv2d_fwd(const hrv_conv_params* p, hrv_stream stream) {
     const cuuint64_t cin_k = (cuuint64_t)a.chunks * p->bk, n_pad = (cuuint64_t)a.tiles_n * p->bn;
     cuuint64_t dims[3] = {cin_k, n_pad, (cuuint64_t)taps};
     cuuint64_t strides[2] = {cin_k * elem, n_pad * cin_k * elem};
-    cuuint32_t box[3] = {(cuuint32_t)p->bk, (cuuint32_t)(pixn ? 128 : p->bn), (cuuint32_t)tpb};  // pixn: rows >= n_pad are zero fill
+    cuuint32_t box[3] = {(cuuint32_t)p->bk, (cuuint32_t)(pixn ? 128 : (pair ? p->bn / 2 : p->bn)), (cuuint32_t)tpb};  // pixn: rows >= n_pad are zero fill; pair: half a tile per CTA
     cuuint32_t es[3] = {1, 1, 1};
     int rc = encode_tensor_map(&a.tmB, 3, const_cast<void*>(p->wpack), dims, strides, box, es, sw);
     if (rc) return rc;
@@ -965,10 +1377,26 @@ extern "C" int hrv_conv2d_fwd(const hrv_conv_params* p, hrv_stream stream) {
     if (a.pairs < gridp) gridp = a.pairs;
     return launch_pixn(a, gridp, smem_p, st);
   }
-  size_t smem = 3072 + (halo ? (size_t)a.stages * a.a_stage_bytes + (size_t)a.sb_stages * a.b_stage_bytes
+  size_t smem = 3072 + tab_bytes + (halo ? (size_t)a.stages * a.a_stage_bytes + (size_t)a.sb_stages * a.b_stage_bytes
                              : (size_t)a.stages * (128 * row_bytes + (((uint32_t)p->bn * row_bytes + 1023u) & ~1023u)));
   if (smem < 120 * 1024) smem = 120 * 1024;  // force one CTA per SM (TMEM: up to 512 columns per CTA)
 
+  if (pair) {
+    static bool attr_done = false;
+    if (!attr_done) {
+      cudaError_t e = cudaFuncSetAttribute(conv_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+      if (e != cudaSuccess) return set_error(HRV_ECUDA, "cudaFuncSetAttribute(conv_pair): %s", cudaGetErrorString(e));
+      attr_done = true;
+    }
+    const long long tiles_m = (long long)a.tiles_x * a.tiles_y * a.tiles_img;
+    const long long items = (long long)a.tiles_n * ((tiles_m + 1) / 2);
+    int clusters = sm_count() / 2;
+    if (items < clusters) clusters = (int)items;
+    conv_pair_kernel<<<2 * clusters, kThreadsC, smem, st>>>(a);  // __cluster_dims__(2,1,1): one pair per TPC
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error(HRV_ECUDA, "conv_pair launch: %s", cudaGetErrorString(e));
+    return HRV_OK;
+  }
   const long long total = (long long)a.tiles_n * a.tiles_x * a.tiles_y * a.tiles_img;
   int grid = sm_count();
   if (total < grid) grid = (int)total;

@@ -154,6 +154,21 @@ def pick_bn(n_gemm):
     return best
 
 
+def pick_bn_spade(n_gemm):
+    """N tile of a gamma|beta GEMM (n_gemm = 2C interleaved columns).  With several N tiles the staged epilogue of the CTA-pair kernel
+    needs each tile's channel range to end on a 16-channel slab, i.e. bn % 32 == 0: take the candidate with the fewest padded columns
+    (ties: the wider tile)."""
+    n16 = round_up(n_gemm, 16)
+    if n16 <= 256:
+        return n16
+    best = None
+    for bn in (256, 224, 192, 160):
+        cols = round_up(n_gemm, bn)
+        if best is None or cols < best[0]:
+            best = (cols, bn)
+    return best[1]
+
+
 @dataclass
 class PackedConv:
     w: torch.Tensor  # bf16 [taps, n_pad, cin_k]
@@ -187,7 +202,8 @@ def pack_weight(w, off, cin_total=None, interleave=None, bn=None, flops_per_pixe
     # Cout <= 128: eligible for the pixel-N kernel (conv_pixn_kernel), which needs 64-channel K blocks (zero padded)
     bk = 64 if (rows <= 128 and k_eff > 32) else pick_bk(k_eff)  # K <= 32 stays on the 32-wide blocks (padding to 64 would double the MMAs)
     cin_k = round_up(k_eff, bk)
-    bn = pick_bn(rows) if bn is None else bn
+    if bn is None:
+        bn = pick_bn_spade(rows) if (interleave is not None and not dgrad) else pick_bn(rows)
     n_pad = round_up(rows, bn)
     wp = torch.empty((kh * kw, n_pad, cin_k), dtype=STORAGE[0], device=w.device)
     with _Timed("glue", 0.0, label="pack_conv_weight"):

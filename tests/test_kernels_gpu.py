@@ -515,3 +515,59 @@ def test_conv_wgrad_is_bit_reproducible():
         ref = torch.nn.grad.conv2d_weight(x.buf[..., :cin].permute(0, 3, 1, 2).float(), (cout, cin, k, k),
                                           dy.buf[..., :cout].permute(0, 3, 1, 2).float(), padding=k // 2)
         assert rel_err(a, ref) < 2e-3
+
+
+PAIR_CASES = [  # spade, cin, n_gemm, h, w, batch, x0_shift, c1 (x1 channels)
+    (True, 128, 160, 64, 48, 2, 0, 0), (True, 128, 160, 64, 48, 2, 1, 16), (True, 128, 288, 48, 32, 3, 1, 16),
+    (True, 128, 544, 64, 48, 2, 1, 16),    # bn 192: two TMEM accumulators, two owner warpgroups
+    (True, 128, 2080, 16, 12, 2, 1, 16),   # 13 N tiles, more channels than the shared-memory constant table holds (global-load path)
+    (True, 128, 144, 30, 22, 1, 0, 0),     # odd number of pixel tiles: the pair's second CTA runs a tile past the end
+    (False, 160, 160, 50, 37, 3, 0, 0), (False, 256, 256, 64, 48, 2, 0, 0), (False, 80, 192, 128, 96, 1, 0, 0)]
+
+
+@pytest.mark.parametrize("case", PAIR_CASES)
+def test_conv_pair_kernel_matches_single_cta_kernel(case):
+    """The CTA-pair kernel (tcgen05 cta_group::2: M = 256 over two SMs, each CTA holding half of every weight stage; epilogue
+    warpgroup w drains accumulator w) against the one-CTA kernel on identical inputs (HRV_CONV_PAIR=0).  Same products, and — when the
+    one-CTA kernel also runs its halo mainloop (SPADE / bn <= 208) — the same fp32 accumulation order: bit-identical outputs, gamma
+    included.  For the 256-column GEMMs the one-CTA kernel walks K tap by tap: equal to one bf16 ulp."""
+    spade, cin, ng, h, w, B, shift, c1 = case
+    g = torch.Generator().manual_seed(1)
+    rnd = lambda *s: torch.randn(*s, generator=g)
+    x = Act(rnd(B, h, w, ops.round_up(cin, 8)).to(torch.bfloat16).to(DEV), c=cin)
+    outs = []
+    try:
+        os.environ["HRV_CONV_PIXN"] = "0"
+        if spade:
+            C = ng // 2
+            pw = ops.pack_weight((rnd(C, cin, 3, 3) * 0.05).to(DEV), (1, 1), interleave=(rnd(C, cin, 3, 3) * 0.05).to(DEV))
+            x0 = Act(rnd(B, h >> shift, w >> shift, C - c1).to(torch.bfloat16).to(DEV))
+            x1 = Act(rnd(B, h, w, c1).to(torch.bfloat16).to(DEV)) if c1 else None
+            mean, rstd = (rnd(B, C) * 0.1).to(DEV), (torch.rand(B, C, generator=g) + 0.5).to(DEV)
+            noise, ns, sh = rnd(B, h, w).to(DEV), (rnd(C) * 0.1).to(DEV), (rnd(2 * C) * 0.1).to(DEV)
+        else:
+            pw = ops.pack_weight((rnd(ng, cin, 3, 3) * 0.05).to(DEV), (1, 1))
+            bias = rnd(ng).to(DEV)
+        if pw.bk != 64:
+            pytest.skip("the pair kernel needs 64-channel K blocks")
+        for flag in ("0", "1"):
+            os.environ["HRV_CONV_PAIR"] = flag
+            if spade:
+                out, gam = Act.empty(B, h, w, C, zero=True), Act.empty(B, h, w, C, zero=True)
+                ops.conv2d_spade(x, pw, out, x0, shift, x1, mean, rstd, noise, ns, sh, 2, gamma_out=gam)
+                torch.cuda.synchronize()
+                outs.append((out.buf.float().clone(), gam.buf.float().clone()))
+            else:
+                out = Act.empty(B, h, w, ng, zero=True)
+                ops.conv2d(x, pw, out, act=2, shift=bias)
+                torch.cuda.synchronize()
+                outs.append((out.buf.float().clone(), None))
+    finally:
+        os.environ.pop("HRV_CONV_PAIR", None)
+        os.environ.pop("HRV_CONV_PIXN", None)
+    (a, ga), (b, gb) = outs
+    d = float((a - b).abs().max())
+    if spade or pw.bn <= 208:
+        assert d == 0.0 and (ga is None or float((ga - gb).abs().max()) == 0.0)
+    else:
+        assert d <= 2 ** -7 * float(a.abs().max())

@@ -29,7 +29,7 @@ class _Loader:
         self.batch = {"agnostic": b["agnostic"], "parse": b["parse"], "densepose": b["densepose"], "parse_cloth": b["parse_cloth"],
                       "parse_agnostic": b["parse_agnostic"], "pcm": b["pcm"], "cloth_mask": {"paired": b["cloth_mask"], "unpaired": b["cloth_mask"]},
                       "cloth": {"paired": b["cloth"], "unpaired": b["cloth"]}, "image": b["image"], "pose": b["densepose"],
-                      "parse_onehot": b["parse_onehot"][:, 0].long()}
+                      "parse_onehot": b["parse_onehot"]}  # (N,1,H,W) class ids, as cp_dataset.py:228 provides them
 
     def next_batch(self):
         return self.batch
@@ -55,7 +55,7 @@ def test_train_generator_loop_unchanged():
     tg = hrv_env.load_reference_script("train_generator")
     assert tg.SPADEGenerator is network_generator.SPADEGenerator and tg.ConditionGenerator is networks.ConditionGenerator
     h, w = 512, 384
-    opt = _opt(tg, ["--name", "t", "--gpu_ids", "0", "-b", "1", "--fine_height", str(h), "--fine_width", str(w), "--keep_step", "2",
+    opt = _opt(tg, ["--name", "t", "--cuda", "True", "--gpu_ids", "0", "-b", "1", "--fine_height", str(h), "--fine_width", str(w), "--keep_step", "2",
                     "--decay_step", "0", "--display_count", "1000", "--save_count", "1000", "--tensorboard_count", "1000",
                     "--lpips_count", "1000", "--occlusion"])
     torch.manual_seed(0)

@@ -66,3 +66,10 @@ for cin, ng, k, h, w, spade in cases:
     print("%4d->%4d k%d %4dx%-4d %-7s %8.3f %8.1f |           %5.1f%% %5.1f%% %5.1f%% %5.1f%% |           %5.1f%% %5.1f%% |              %5.1f%%   (%d CTAs, %.0f tiles/CTA, %.0f cyc/tile)"
           % (cin, ng, k, h, w, "spade" if spade else "linear", ms, fl / ms / 1e9, 100 * (1 - f(1) - f(2) - f(3)), 100 * f(1), 100 * f(2), 100 * f(3),
              100 * f(4), 100 * f(5), 100 * float(s[:, 6].mean() / s[:, 7].mean()), s.shape[0], float(s[:, 8].mean()), float(tot / s[:, 8].mean())), flush=True)
+    if float(s[:, 11:16].sum()) > 0:
+        life = s[:, 7].mean()
+        print("      staged epilogue, warp 4: x-load issue %.1f%% | wait accumulator %.1f%% | wait x %.1f%% | drain+barrier %.1f%% | chunks %.1f%% | fence+barrier+store %.1f%%" %
+              tuple(100 * float(s[:, i].mean() / life) for i in (11, 12, 13, 14, 15, 9)), flush=True)
+    elif float(s[:, 9].sum()) > 0 or float(s[:, 10].sum()) > 0:
+        print("      epilogue warp 4 of the pair kernel: %.1f%% of its life issuing the x prefetch, %.1f%% in tcgen05.ld + wait::ld" %
+              (100 * float(s[:, 9].mean() / s[:, 7].mean()), 100 * float(s[:, 10].mean() / s[:, 7].mean())), flush=True)
