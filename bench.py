@@ -702,7 +702,23 @@ def main():
             line["cpu_baseline"] = cpu_baseline
         print(json.dumps(line))
     if world > 1:
+        # Tear-down.  The result is already on stdout; nothing below may keep the job alive.  Graph nodes reference the NCCL
+        # communicator (round 2: both 2-GPU graph runs printed their line and then sat in destroy_process_group until `timeout`
+        # killed them), so the graph goes first, and a watchdog ends the process if the communicator still refuses to die.
+        sys.stdout.flush()
+        wd = threading.Timer(45.0, lambda: os._exit(0))
+        wd.daemon = True
+        wd.start()
+        torch.cuda.synchronize()
+        barrier()
+        if train and use_graph:
+            trainer.release_graph()
         dist.destroy_process_group()
+        wd.cancel()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    if world > 1:
+        os._exit(0)  # skip interpreter-exit destructors of NCCL-bearing objects (same hang, later)
 
 
 if __name__ == "__main__":

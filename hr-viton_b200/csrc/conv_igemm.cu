@@ -1249,7 +1249,9 @@ extern "C" int hrv_conv2d_fwd(const hrv_conv_params* p, hrv_stream stream) {
   // CTA-pair kernel (cta_group::2, M = 256 over two SMs, each CTA holds half of every weight stage): wide-N 3x3 GEMMs whose one-CTA
   // form is bound by shared-memory bandwidth.  Needs the halo mainloop, 64-channel K blocks and an even SM count.
   const char* env_pair = getenv("HRV_CONV_PAIR");  // read per call (tests compare the two kernels on identical inputs)
-  const bool pair_shape = p->bk == 64 && p->bn >= 144 && p->bn <= 256 && (p->bn % 16) == 0 && out.h >= 12 && p->kh * p->kw > 1 && !pixn;
+  const char* env_minbn = getenv("HRV_CONV_PAIR_MINBN");  // experiment knob (tools/conv_stall_probe.py): narrower tiles in pair mode
+  const int pair_min_bn = env_minbn ? atoi(env_minbn) : 144;
+  const bool pair_shape = p->bk == 64 && p->bn >= pair_min_bn && p->bn >= 32 && p->bn <= 256 && (p->bn % 16) == 0 && out.h >= 12 && p->kh * p->kw > 1 && !pixn;
   const bool pair = pair_shape && !(env_pair && env_pair[0] == '0') && !(force && force[0] == '0') && (sm_count() % 2) == 0;
   if (pair) halo = true;
   const int TW = halo ? 8 : pick_pow2(out.w, 128);

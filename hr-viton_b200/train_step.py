@@ -182,6 +182,16 @@ class _GraphMixin:
         ops.PARAM_GEN[0] += 1  # the replayed optimiser step changed parameters without touching tensor._version: derived caches are stale
         return self._graph_out
 
+    def release_graph(self):
+        """Destroy the captured graph (its nodes hold references on the NCCL communicator: ncclCommDestroy at process-group
+        tear-down waits for them — the round-2 two-GPU runs printed their result and then hung in destroy_process_group)."""
+        torch.cuda.synchronize()
+        self._graph = None
+        self._graph_out = None
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+
 
 class Stage2Trainer(_GraphMixin):
     """Holds the optimisers / criteria of train_generator.py:145-159 and runs one step."""

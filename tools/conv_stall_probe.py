@@ -23,7 +23,10 @@ stats = torch.zeros(148 * 16, dtype=torch.int64, device="cuda")
 cases = [  # cin, n_gemm, k, h, w, spade
     (128, 160, 3, 1024, 768, True), (128, 288, 3, 512, 384, True), (128, 544, 3, 256, 192, True), (128, 64, 3, 1024, 768, True),
     (160, 160, 3, 1024, 768, False), (256, 256, 3, 256, 192, False), (512, 512, 3, 128, 96, False), (1040, 512, 3, 64, 48, False),
-    (80, 160, 3, 1024, 768, False)]
+    (80, 160, 3, 1024, 768, False), (160, 128, 3, 1024, 768, False), (288, 128, 3, 512, 384, False), (128, 128, 3, 512, 384, False),
+    (64, 64, 3, 1024, 768, False)]
+if os.environ.get("HRV_PROBE_CASES"):  # e.g. "9,10,11,3"
+    cases = [cases[int(i)] for i in os.environ["HRV_PROBE_CASES"].split(",")]
 os.environ["HRV_CONV_PIXN"] = "0"
 print("%-34s %8s %8s | MMA warp: %6s %6s %6s %6s | producer: %6s %6s | epilogue w4: %6s" %
       ("layer", "ms", "TFLOP/s", "issue", "waitA", "waitB", "waitD", "freeA", "freeB", "waitAcc"))
