@@ -35,10 +35,15 @@ def gen_opt():
                                  fine_height=H, fine_width=W, cuda=True)
 
 
+TRAIN_STAGE2_WORKLOAD = ("train_stage2: full train_generator.py step (tocg fwd, G fwd+bwd, D fwd+bwd x2, 2nd G fwd, VGG loss fwd+dgrad, "
+                         "Adam x2), 1024x768")
+
+
 def conv_traffic():
     """Average DRAM bytes (read+write) per conv_igemm launch of one step, from the committed ncu pass
-    (profiles/r1_conv_dram_traffic.json, written by tools/summarise_ncu_traffic.py); None when that pass was not taken."""
-    p = os.path.join(ROOT, "profiles", "r1_conv_dram_traffic.json")
+    (profiles/r2_conv_dram_traffic.json, written by tools/summarise_ncu_traffic.py from the ncu launch list of one step of the default
+    command); None when that pass was not taken."""
+    p = os.path.join(ROOT, "profiles", "r2_conv_dram_traffic.json")
     try:
         with open(p) as f:
             return json.load(f)["avg_dram_bytes_per_launch"]
@@ -280,15 +285,51 @@ def build_reference_nets(ref, h, w, device):
     return (tocg, G, D, vgg), {"tocg": topt}, opt_g, opt_d
 
 
+def host_threads():
+    """Threads the CPU arm should use: the cores this process may actually run on — scheduler affinity, the cgroup CPU quota and
+    the number of PHYSICAL cores behind the affinity mask, whichever is smallest.  (Round 2, first try: os.cpu_count() = 128 hardware
+    threads on the GPU box made one reference step take 139 s — slower than the same step on 8 cores of the build container, 31 s:
+    oversubscribed OpenMP teams.)"""
+    try:
+        aff = sorted(os.sched_getaffinity(0))
+    except AttributeError:
+        aff = list(range(os.cpu_count() or 1))
+    n = len(aff)
+    try:  # cgroup v2 quota
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            n = min(n, max(1, int(float(q) / float(per) + 0.5)))
+    except Exception:
+        pass
+    try:  # physical cores among the allowed logical CPUs
+        cores, cur = set(), {}
+        for ln in open("/proc/cpuinfo"):
+            if ":" in ln:
+                k, v = [t.strip() for t in ln.split(":", 1)]
+                cur[k] = v
+            elif cur:
+                if int(cur.get("processor", -1)) in aff:
+                    cores.add((cur.get("physical id", "0"), cur.get("core id", cur.get("processor"))))
+                cur = {}
+        if cores:
+            n = min(n, len(cores))
+    except Exception:
+        pass
+    env = os.environ.get("HRV_REF_THREADS")
+    return max(1, int(env)) if env else max(1, n)
+
+
 def cpu_baseline_train(steps=3, warmup=1, budget_s=200.0, size=(512, 384)):
     """The reference's own modules (baseline/_ref) running one REAL train_generator.py step per timed step on the host cores: tocg
     fwd (256x192, as in the reference) -> glue -> G fwd+bwd -> D -> hinge/feature-matching/VGG -> Adam(G) -> 2nd G fwd -> D fwd+bwd ->
-    Adam(D), fp32, batch 1 at 512x384 — a quarter of the benchmarked pixel count, the smallest 4:3 size the generator admits (multiples
-    of 128).  Reported as 1024x768-equivalent images/s (x 1/4: the three networks are fully convolutional, cost scales with pixels;
-    the 256x192 tocg is NOT scaled down, which favours the CPU slightly).  Falls back to the oracle port's generator fwd+bwd
-    (kind 'port') only when no reference checkout travelled with the tree."""
+    Adam(D), fp32, batch 1 at 512x384 — a quarter of the benchmarked pixel count and the smallest 4:3 size the reference generator
+    admits (its latent grid is fine_width // 128 wide).  Reported as 1024x768-equivalent images/s (x 1/4: the three networks are fully
+    convolutional, cost scales with pixels; the 256x192 tocg is NOT scaled down, which favours the CPU slightly).
+    `warmup` / `steps` are honoured while the wall budget lasts: the loop stops early (never before one warm-up and one timed step)
+    when the next step would overrun `budget_s`; what was actually run is returned and printed.  Falls back to the oracle port's
+    generator fwd+bwd (kind 'port') only when no reference checkout travelled with the tree."""
     import torch
-    cores = os.cpu_count() or 1
+    cores = host_threads()
     torch.set_num_threads(cores)
     ref = _reference_modules()
     if ref is None:
@@ -299,22 +340,28 @@ def cpu_baseline_train(steps=3, warmup=1, budget_s=200.0, size=(512, 384)):
     h, w = size
     nets, opts, opt_g, opt_d = build_reference_nets(ref, h, w, "cpu")
     batch = train_step.synthetic_batch(1, h, w, "cpu", seed=100)
-    times = []
+    times, warm_done = [], 0
     t_begin = time.time()
-    for i in range(warmup + steps):
+    warmup = max(1, warmup)  # the first step pays oneDNN primitive creation (2-3x a steady step)
+    while len(times) < steps:
         t0 = time.time()
         reference_stage2_step(nets, opts, batch, h, w, opt_g, opt_d)
         dt = time.time() - t0
-        if i >= warmup:
-            times.append(dt)
-        if times and time.time() - t_begin + dt > budget_s:
+        elapsed = time.time() - t_begin
+        if warm_done < warmup:
+            warm_done += 1
+            if (budget_s - elapsed) < (warmup - warm_done + steps) * dt * 0.6:
+                warmup = warm_done  # budget: spend what is left on timed steps, not on more warm-ups
+            continue
+        times.append(dt)
+        if elapsed + dt > budget_s:
             break
     mean = sum(times) / len(times)
     scale = (h * w) / float(H * W)
     return {"value": scale / mean, "unit": "images/s", "cores": cores, "kind": "reference",
             "sample": "UNMODIFIED reference modules (%s), one full train_generator.py step per timed step, fp32, batch 1 at %dx%d (%.3g of the 1024x768 pixels; value = %.3g / step seconds), %d warm-up + %d timed steps, mean %.2f s/step, torch %s CPU, %d threads"
-                      % (os.path.relpath(ref[2], ROOT) if ref[2].startswith(ROOT) else ref[2], h, w, scale, scale, warmup, len(times), mean, torch.__version__, cores),
-            "s_per_step": mean, "steps_done": len(times), "warmup_done": warmup, "pixel_scale": scale}
+                      % (os.path.relpath(ref[2], ROOT) if ref[2].startswith(ROOT) else ref[2], h, w, scale, scale, warm_done, len(times), mean, torch.__version__, cores),
+            "s_per_step": mean, "steps_done": len(times), "warmup_done": warm_done, "pixel_scale": scale}
 
 
 def _cpu_baseline_port():
@@ -342,24 +389,33 @@ def _cpu_baseline_port():
 
 
 def run_reference(args):
+    """The driver's reference arm: the UNMODIFIED reference modules on the host cores (module docstring, cpu_baseline_train).  One
+    timed step = one real train_generator.py step on a bounded sample (batch 1 at 512x384 = 0.25 image-equivalents of 1024x768);
+    `ms_per_step` is the MEASURED wall time of such a step, `value` = 0.25 / that.  --steps / --warmup are honoured up to a wall
+    budget (--ref-budget-s, default 240 s) so the arm ends within a few minutes whatever the box's cores; `steps` / `warmup` in the
+    line are what actually ran (the requests are kept beside them)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    budget = float(os.environ.get("HRV_REF_BUDGET_S", "240"))
     if args.workload in ("train_stage2", "pipeline"):
-        cb = cpu_baseline_train(steps=max(1, args.steps), warmup=max(1, min(args.warmup, 1)))
-        wl = ("train_stage2: full train_generator.py step, reference modules on the host CPU, batch 1 at 512x384 = 1/4 of the 1024x768 pixels "
-              "(value and ms_per_step are per 1024x768-equivalent image: measured step seconds x 4)")
-        ms = cb["s_per_step"] / cb["pixel_scale"] * 1e3
+        cb = cpu_baseline_train(steps=max(1, args.steps), warmup=max(1, args.warmup), budget_s=budget)
+        wl = TRAIN_STAGE2_WORKLOAD
+        ms = cb["s_per_step"] * 1e3
+        per_step = cb["pixel_scale"]
     else:
         cb = cpu_baseline_gen(steps=max(1, args.steps), warmup=min(args.warmup, 1))
         cb["warmup_done"] = min(args.warmup, 1)
-        wl = "gen_fwd: SPADEGenerator inference forward 1024x768 (reference algorithm, host CPU, 1 image per step)"
+        wl = "gen_fwd: SPADEGenerator inference forward, 1024x768, bf16 activations, fp32 accumulate"
         ms = cb["s_per_image"] * 1e3
+        per_step = 1.0
     line = {"impl": "reference", "metric": "1024x768 try-on images/sec", "value": cb["value"], "unit": "images/s", "n_gpus": args.gpus,
             "steps": cb["steps_done"], "warmup": cb["warmup_done"], "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl, "measured_wall_s_per_step": cb.get("s_per_step", cb.get("s_per_image")),
-                       "steps_requested": args.steps, "note": "steps are capped so that the arm finishes in ~3-4 minutes of CPU time"},
+            "config": {"workload": wl, "launch": "eager, host CPU (%d threads)" % cb["cores"], "feeding": "host tensors",
+                       "per_gpu_batch": 8, "global_batch": 8, "parallelism": "dp1",
+                       "sample": cb["sample"], "images_per_step": per_step,
+                       "steps_requested": args.steps, "warmup_requested": args.warmup, "wall_budget_s": budget},
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -687,9 +743,11 @@ def main():
                 "ms_per_step": ms / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "bf16",
                 "data": "synthetic",
                 "config": {"workload": ("train_stage1: full train_condition.py step (tocg fwd+bwd with train-mode BatchNorm, 3 stage-1 D passes fwd+bwd, VGG loss x5 fwd+dgrad, L1/TV/CE/LSGAN, Adam x2; README flags --Ddownx2 --Ddropout --lasttvonly --interflowloss --occlusion), 1024x768, bf16 activations / fp32 accumulate" if (train and stage1) else
-                                        "train_stage2: full train_generator.py step (tocg fwd, G fwd+bwd, D fwd+bwd x2, 2nd G fwd, VGG loss fwd+dgrad, Adam x2), 1024x768, bf16 activations / fp32 accumulate; convs (fwd/dgrad/wgrad), norms, modulation, activations, pooling, weight packing, parse-map glue, VGG L1 on this repo's kernels; hi-res grid_sample, hinge/feature-matching reductions, spectral-norm power iteration, Adam = torch"
+                                        TRAIN_STAGE2_WORKLOAD
                                         if train else ("pipeline: end-to-end test_generator.py inference (tocg 256x192 -> parse post-processing -> hi-res cloth warp with occlusion handling -> SPADEGenerator), 1024x768, bf16 activations / fp32 accumulate"
                                                        if pipe else "gen_fwd: SPADEGenerator inference forward, 1024x768, bf16 activations, fp32 accumulate")),
+                           "kernels": ("bf16 activations / fp32 accumulate; convs (fwd/dgrad/wgrad), norms, modulation, activations, pooling, weight packing, parse-map and warp glue, VGG L1 on this repo's kernels; hinge/feature-matching reductions, spectral-norm power iteration, Adam = torch"
+                                       if (train and not stage1) else "this repo's kernels (see DESIGN.md)"),
                            "launch": (("cuda-graph replay of the whole step" + (" (NCCL bucket all-reduces captured in the graph)" if world > 1 else "")) if (train and use_graph) else "eager"),
                            "feeding": "e2e: pinned host batch -> device on a copy stream, double-buffered (overlaps the previous step); one-hot parse maps shipped as uint8 labels and expanded by hrv_onehot_u8" if train else "e2e: pinned host -> device on the compute stream", "per_gpu_batch": B, "global_batch": B * world, "parallelism": "dp%d" % world,
                            "l2": "activations per step (>10 GB) exceed the 126 MB L2; no explicit flush",

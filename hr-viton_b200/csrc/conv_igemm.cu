@@ -1232,27 +1232,38 @@ extern "C" int hrv_conv2d_fwd(const hrv_conv_params* p, hrv_stream stream) {
   memset(&a, 0, sizeof(a));
   a.Nimg = out.n; a.Hout = out.h; a.Wout = out.w;
   a.stats = g_conv_stats;
+  const char* force = getenv("HRV_CONV_HALO");  // read per call (tests / A-B runs flip it)
+  // CTA-pair kernel (cta_group::2, M = 256 over two SMs, each CTA holds half of every weight stage): 3x3 GEMMs whose one-CTA form is
+  // bound by shared-memory bandwidth (profiles/r2_conv_stall_*.txt: +20..65 % for every tile width from 64 to 256 columns).  Needs
+  // the halo mainloop, 64-channel K blocks and an even SM count.
+  const char* env_pair = getenv("HRV_CONV_PAIR");        // read per call (tests compare the two kernels on identical inputs)
+  const char* env_minbn = getenv("HRV_CONV_PAIR_MINBN");  // A-B knobs (tools/conv_stall_probe.py, bench.py)
+  const char* env_over = getenv("HRV_CONV_PAIR_OVER_PIXN_MAXBN");
+  const int pair_min_bn = env_minbn ? atoi(env_minbn) : 32;
+  const int pair_over_pixn = env_over ? atoi(env_over) : 64;
+  const bool pair_geom = p->bk == 64 && p->bn >= pair_min_bn && p->bn >= 32 && p->bn <= 256 && (p->bn % 16) == 0 && out.h >= 12 && p->kh * p->kw > 1;
+  const bool pair_ok = pair_geom && !(env_pair && env_pair[0] == '0') && !(force && force[0] == '0') && (sm_count() % 2) == 0;
   // Pixel-N variant (weights as the M operand, 256 pixels as N): few output channels, plain bf16 NHWC output.
   const char* env_pixn = getenv("HRV_CONV_PIXN");  // read per call: tests flip it to compare the two kernels on identical inputs
-  const bool pixn = !(env_pixn && env_pixn[0] == '0') && p->epi == HRV_EPI_LINEAR && p->bk == 64 && p->n_gemm <= 128 &&
+  const bool pixn_ok = !(env_pixn && env_pixn[0] == '0') && p->epi == HRV_EPI_LINEAR && p->bk == 64 && p->n_gemm <= 128 &&
                     out.dtype == HRV_BF16 && p->out_layout == HRV_NHWC && (!p->res.ptr || p->res_mode != 0) && in.c > 32 &&
                     ((out.c + 7) & ~7) <= out.pitch && ((out.c + 7) & ~7) <= 128;
+  // Both kernels can run a narrow 3x3 GEMM.  Measured per layer inside the train step (profiles/r2_kernel_selection_ab.txt): the pair
+  // kernel wins for <= 64 columns fed by more than 64 channels (144->64 -14 %, 128->64 -16 %, 80->32 -29 %) and whenever the
+  // pixel-N kernel's 256-pixel tiles cannot fill the SMs (2080->128 at 32x24: -39 %); pixel-N wins for 64->64 (+21 % if moved), the
+  // 2x2 space-to-depth convolutions and everything with 128 columns at 128x96 and above.
+  const long long pixn_tiles = ((long long)out.n * out.h * out.w + 255) / 256;
+  const bool pair_beats_pixn = pair_ok && ((p->bn <= pair_over_pixn && p->kh * p->kw == 9 && in.c > 64 && !p->res.ptr) || pixn_tiles < sm_count());
+  const bool pixn = pixn_ok && !pair_beats_pixn;
   // Halo mode (one (16+KH-1)x(8+KW-1) box per channel chunk, taps as shifted descriptor views) whenever the image is
   // tall enough for a 16x8 single-image tile; tap-by-tap mode (tile may span images) for the tiny pyramid levels.
-  const char* force = getenv("HRV_CONV_HALO");  // read per call (tests / A-B runs flip it)
   // Measured on B200 (tools/conv_bench.py, profiles/conv_variants_r1.txt): the halo path wins for narrow GEMMs
   // (N <= 32: 1.3-1.45x) and for the 144..208-column SPADE gamma/beta GEMMs (+5%); tap-by-tap wins for 1x1 and N=256.
   const bool halo_shape = (p->bn <= 32) || (p->bk == 16) || (p->bk == 64 && p->bn >= 144 && p->bn <= 208);
   bool halo = out.h >= 12 && p->kh * p->kw > 1 && halo_shape && !pixn;
   if (force && force[0] == '0') halo = false;
   if (force && force[0] == '1') halo = true;
-  // CTA-pair kernel (cta_group::2, M = 256 over two SMs, each CTA holds half of every weight stage): wide-N 3x3 GEMMs whose one-CTA
-  // form is bound by shared-memory bandwidth.  Needs the halo mainloop, 64-channel K blocks and an even SM count.
-  const char* env_pair = getenv("HRV_CONV_PAIR");  // read per call (tests compare the two kernels on identical inputs)
-  const char* env_minbn = getenv("HRV_CONV_PAIR_MINBN");  // experiment knob (tools/conv_stall_probe.py): narrower tiles in pair mode
-  const int pair_min_bn = env_minbn ? atoi(env_minbn) : 144;
-  const bool pair_shape = p->bk == 64 && p->bn >= pair_min_bn && p->bn >= 32 && p->bn <= 256 && (p->bn % 16) == 0 && out.h >= 12 && p->kh * p->kw > 1 && !pixn;
-  const bool pair = pair_shape && !(env_pair && env_pair[0] == '0') && !(force && force[0] == '0') && (sm_count() % 2) == 0;
+  const bool pair = pair_ok && !pixn;
   if (pair) halo = true;
   const int TW = halo ? 8 : pick_pow2(out.w, 128);
   const int TH = halo ? 16 : pick_pow2(out.h, 128 / TW);

@@ -24,10 +24,11 @@ cases = [  # cin, n_gemm, k, h, w, spade
     (128, 160, 3, 1024, 768, True), (128, 288, 3, 512, 384, True), (128, 544, 3, 256, 192, True), (128, 64, 3, 1024, 768, True),
     (160, 160, 3, 1024, 768, False), (256, 256, 3, 256, 192, False), (512, 512, 3, 128, 96, False), (1040, 512, 3, 64, 48, False),
     (80, 160, 3, 1024, 768, False), (160, 128, 3, 1024, 768, False), (288, 128, 3, 512, 384, False), (128, 128, 3, 512, 384, False),
-    (64, 64, 3, 1024, 768, False)]
+    (64, 64, 3, 1024, 768, False), (80, 32, 3, 1024, 768, False), (32, 32, 3, 1024, 768, False), (144, 64, 3, 512, 384, False),
+    (128, 128, 3, 512, 384, True), (32, 80, 3, 1024, 768, False)]
 if os.environ.get("HRV_PROBE_CASES"):  # e.g. "9,10,11,3"
     cases = [cases[int(i)] for i in os.environ["HRV_PROBE_CASES"].split(",")]
-os.environ["HRV_CONV_PIXN"] = "0"
+os.environ.setdefault("HRV_CONV_PIXN", "0")  # default: probe the classic / pair kernels; HRV_CONV_PIXN=1 lets the dispatcher choose
 print("%-34s %8s %8s | MMA warp: %6s %6s %6s %6s | producer: %6s %6s | epilogue w4: %6s" %
       ("layer", "ms", "TFLOP/s", "issue", "waitA", "waitB", "waitD", "freeA", "freeB", "waitAcc"))
 for cin, ng, k, h, w, spade in cases:
@@ -46,16 +47,17 @@ for cin, ng, k, h, w, spade in cases:
         pw = ops.pack_weight(wt, (k // 2, k // 2))
         out = Act.empty(B, h, w, ng)
         fn = lambda: ops.conv2d(x, pw, out)
-    for _ in range(3):
+    IT = int(os.environ.get("HRV_PROBE_ITERS", "5"))  # 0: exactly one launch per layer (ncu --set full captures)
+    for _ in range(3 if IT else 0):
         fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(5):
+    for _ in range(IT):
         fn()
     e1.record()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 5
+    ms = e0.elapsed_time(e1) / max(IT, 1) if IT else 1.0
     stats.zero_()
     L.hrv_debug_set_conv_stats(ctypes.c_void_p(stats.data_ptr()))
     fn()
@@ -63,6 +65,10 @@ for cin, ng, k, h, w, spade in cases:
     L.hrv_debug_set_conv_stats(None)
     s = stats.view(148, 16).double()
     s = s[s[:, 0] > 0]
+    if s.shape[0] == 0:  # the dispatcher chose a kernel without stall counters (pixel-N): timing only
+        print("%4d->%4d k%d %4dx%-4d %-7s %8.3f %8.1f |   (pixel-N kernel: no stall counters)" %
+              (cin, ng, k, h, w, "spade" if spade else "linear", ms, 2.0 * cin * ng * k * k * B * h * w / ms / 1e9), flush=True)
+        continue
     tot = s[:, 0].mean()
     f = lambda i: float(s[:, i].mean() / tot)
     fl = 2.0 * cin * ng * k * k * B * h * w

@@ -1,5 +1,5 @@
 """Summarise an `ncu --csv --page raw` launch list (metrics gpu__time_duration.sum, dram__bytes_read.sum, dram__bytes_write.sum)
-into (a) per-kernel totals/shares and (b) profiles/r1_conv_dram_traffic.json used by bench.py's roofline.traffic.
+into (a) per-kernel totals/shares and (b) profiles/r2_conv_dram_traffic.json used by bench.py's roofline.traffic.
 Usage: python tools/summarise_ncu_traffic.py <launches.csv> [out.json]"""
 import csv, json, re, sys, collections
 
@@ -54,10 +54,10 @@ print("launches %d  total %.2f ms (serialised, cold-cache)" % (len(rows), tot))
 print("%-70s %7s %10s %7s %12s" % ("kernel", "count", "ms", "share", "dram GB"))
 for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1])[:40]:
     print("%-70s %7d %10.3f %6.1f%% %12.3f" % (k[:70], a[0], a[1], 100 * a[1] / tot, a[2] / 1e9))
-conv = [a for k, a in agg.items() if "conv_igemm_kernel" in k or "conv_pixn_kernel" in k]
+conv = [a for k, a in agg.items() if "conv_igemm_kernel" in k or "conv_pixn_kernel" in k or "conv_pair_kernel" in k]
 if conv and len(sys.argv) > 2:
     n = sum(a[0] for a in conv); b = sum(a[2] for a in conv); ms = sum(a[1] for a in conv)
     if b > 0:
-        json.dump({"kernel": "conv_igemm_kernel + conv_pixn_kernel", "launches": n, "avg_dram_bytes_per_launch": b / n, "total_dram_bytes": b,
+        json.dump({"kernel": "conv_pair_kernel + conv_pixn_kernel + conv_igemm_kernel", "launches": n, "avg_dram_bytes_per_launch": b / n, "total_dram_bytes": b,
                    "total_ms_under_ncu": ms, "source": sys.argv[1]}, open(sys.argv[2], "w"), indent=1)
         print("wrote", sys.argv[2])
