@@ -720,12 +720,31 @@ def main():
     conv_ms = agg.get("conv", [0, 0, 0])[1] + agg.get("conv_spade", [0, 0, 0])[1]
     conv_launches = agg.get("conv", [0, 0, 0])[2] + agg.get("conv_spade", [0, 0, 0])[2]
     achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
-    roofline = {"kernel": "conv_igemm_kernel + conv_pixn_kernel (tcgen05 implicit-GEMM convolution, all %d launches of one step)" % conv_launches,
+    roofline = {"kernel": "conv_pair_kernel + conv_pixn_kernel + conv_igemm_kernel (tcgen05 implicit-GEMM convolution, all %d launches of one step)" % conv_launches,
                 "bound": "tensor", "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["tf_sustained"],
                 "traffic": conv_traffic() if (train and not stage1 and B == 8) else None,  # the ncu pass was taken on the default workload only
                 "peak_source": peaks["src"] + " (bf16 sustained)",
                 "avg_launch_ms": conv_ms / max(1, conv_launches), "algorithmic_gflop_per_launch": conv_flops / 1e9 / max(1, conv_launches)}
+    # The convolution launches are not all tensor-bound: the thin-channel full-resolution layers (3->64, 9->16, 32->3, the 1x1 64->128
+    # after im2col ...) move more bytes than the tensor pipe needs time for.  Second figure: every launch against ITS OWN bound,
+    # max(flops / tensor peak, algorithmic bytes / HBM peak), summed over the step and divided by the measured time.
+    import re
+    floor_ms, n_hbm = 0.0, 0
+    for kind, work, e0, e1, label in prof:
+        if kind not in ("conv", "conv_spade"):
+            continue
+        m = re.match(r"\s*(\d+)->(\d+) k(\d+)x(\d+) n(\d+) (\d+)x(\d+)", label or "")
+        if not m:
+            continue
+        cin, ng, _kh, _kw, nb, hh, ww = (int(v) for v in m.groups())
+        byt = float(nb) * hh * ww * ((cin + ng) * 2 + (4 if kind == "conv_spade" else 0))  # input + output (SPADE: gamma|beta columns <-> x read + out write) [+ noise]
+        t_t, t_h = work / (peaks["tf_sustained"] * 1e12) * 1e3, byt / (peaks["hbm_gbs"] * 1e9) * 1e3
+        floor_ms += max(t_t, t_h)
+        n_hbm += 1 if t_h > t_t else 0
+    if conv_ms > 0:
+        roofline["frac_vs_per_launch_bound"] = floor_ms / conv_ms
+        roofline["hbm_bound_launches"] = n_hbm
     total_prof_ms = sum(a[1] for a in agg.values())
     breakdown = {k: {"ms": round(a[1], 3), "launches": a[2], "share": round(a[1] / total_prof_ms, 4)} for k, a in agg.items()}
     if "instnorm_stats" in agg:

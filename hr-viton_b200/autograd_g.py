@@ -369,8 +369,35 @@ def _s2d_weight_t(w):
     return wp.permute(0, 3, 5, 1, 2, 4).reshape(cout, 4 * cin8, 2, 2)  # channel = (py*2+px)*cin8 + ci, taps (ty,tx)
 
 
-def discriminator_forward_train(D, input_nchw, need_wgrad=True, as_float=True):
-    """MultiscaleDiscriminator.forward with autograd (network_generator.py:293-316); returns NCHW fp32 feature lists."""
+class FeatMatchFn(torch.autograd.Function):
+    """One term of the GAN feature-matching loss (train_generator.py:303-311): mean |D_j(fake) - D_j(real).detach()| where the
+    discriminator ran on the concatenation [fake; real] along the batch axis, so one pixel-major buffer holds both halves.  Forward =
+    hrv_l1_sum over the two halves; backward = hrv_l1_bwd into the first half of a zeroed gradient buffer (the real half carries no
+    gradient).  Replaces four strided torch element-wise passes (sub, abs, sgn*g, slice-backward copy) per feature map."""
+
+    @staticmethod
+    def forward(ctx, buf):
+        half = buf.shape[0] // 2
+        ctx.save_for_backward(buf)
+        a, b = Act(buf[:half]), Act(buf[half:])
+        return (ops.l1_sum(a, b) / float(a.n * a.h * a.w * a.c)).float().reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        (buf,) = ctx.saved_tensors
+        half = buf.shape[0] // 2
+        a, b = Act(buf[:half]), Act(buf[half:])
+        d = torch.empty_like(buf)
+        d[half:].zero_()
+        gscale = (g.float() / float(a.n * a.h * a.w * a.c)).reshape(1).contiguous()
+        ops.l1_bwd(a, b, gscale, out=Act(d[:half]))
+        return d
+
+
+def discriminator_forward_train(D, input_nchw, need_wgrad=True, as_float=True, raw=False):
+    """MultiscaleDiscriminator.forward with autograd (network_generator.py:293-316); returns NCHW fp32 feature lists
+    (raw=True: the pixel-major buffers themselves for the intermediate features — FeatMatchFn's operand — and the NCHW view of the
+    last, 1-channel output)."""
     x = FromNCHW.apply(input_nchw, None, None)
     cin = input_nchw.shape[1]
     result = []
@@ -379,7 +406,10 @@ def discriminator_forward_train(D, input_nchw, need_wgrad=True, as_float=True):
     for k, d in enumerate(ds):
         outs = _nlayer_train(d, cur, need_wgrad)
         feats = []
-        for o in outs:
+        for j, o in enumerate(outs):
+            if raw and j + 1 < len(outs):
+                feats.append(o)
+                continue
             c = o.shape[3] if o.dtype != torch.float32 else 1
             v = o[..., :c].permute(0, 3, 1, 2)  # NCHW view of the pixel-major buffer (no copy)
             feats.append(v.float() if as_float else v)

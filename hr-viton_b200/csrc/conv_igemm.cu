@@ -64,6 +64,7 @@ struct alignas(64) ConvArgs {
   int gamma_pitch;
   int pairs, tiles_m, store_c;  // pixel-N variant: 256-pixel tiles (pairs of 128-pixel boxes), channels written per pixel
   int epi_tab;                  // CTA-pair kernel, SPADE: per-warpgroup constant tables in shared memory
+  int epi_own;                  // one-CTA kernel, LINEAR: accumulator i is drained by epilogue warpgroup i % kEpiC alone (whole tile)
   unsigned long long* stats;    // debug (tools/conv_stall_probe.py): per-CTA cycle counters of the warp roles, or nullptr
 };
 
@@ -435,7 +436,7 @@ __global__ void __launch_bounds__(kThreadsC, 1) conv_igemm_kernel(const __grid_c
     }
     for (int i = 0; i < a.nacc; ++i) {
       mbar_init(bar_tfull(i), 1);
-      mbar_init(bar_tempty(i), 4 * kEpiC);  // one arrival per epilogue warp
+      mbar_init(bar_tempty(i), a.epi_own ? 4 : 4 * kEpiC);  // one arrival per epilogue warp that drains the accumulator
     }
     fence_mbar_init();
   } else if (warp == 2) {
@@ -629,7 +630,17 @@ __global__ void __launch_bounds__(kThreadsC, 1) conv_igemm_kernel(const __grid_c
     const int r = q * 32 + lane;
     const int tw_mask = (1 << a.tw_log) - 1, th_mask = (1 << a.th_log) - 1;
     uint32_t acc = 0, aph = 0;
+    // Owner mode (thin LINEAR tiles): the tile in accumulator i belongs to warpgroup i % kEpiC, which drains all of its columns, so
+    // kEpiC tiles are in their epilogue at once.  With every warpgroup on the same tile the tile period is the LATENCY of one
+    // epilogue (wait -> tcgen05.ld -> convert -> st.global -> arrive: ~2800 cycles, profiles/r2_conv_stall_thin_tiles_ab.txt: every
+    // full-resolution layer with <= 64 columns took 0.54 ms whatever its K and N).  The accumulator count is a multiple of kEpiC
+    // (host), so a barrier always meets the same waiter in consecutive phases (mbarrier parity cannot tell phases two apart).
+    const bool own = a.epi_own != 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      if (own && (int)(acc % (uint32_t)kEpiC) != wg) {
+        if (++acc == NACC) { acc = 0; aph ^= 1u; }
+        continue;
+      }
       const int nt = tile % a.tiles_n;
       int mt = tile / a.tiles_n;
       const int tx = mt % a.tiles_x;
@@ -649,7 +660,8 @@ __global__ void __launch_bounds__(kThreadsC, 1) conv_igemm_kernel(const __grid_c
       if (a.epi == 0) {
         mbar_wait_acct(bar_tfull(acc), aph, acct, w0);
         tc_fence_after();
-        epi_linear(a, et, wg);
+        if (own) epi_linear(a, et, 0, 1);
+        else epi_linear(a, et, wg);
       } else {
         uint4 xv[kMaxChunks];
         float nz;
@@ -1278,6 +1290,9 @@ extern "C" int hrv_conv2d_fwd(const hrv_conv_params* p, hrv_stream stream) {
   a.BN = p->bn; a.n_gemm = p->n_gemm;
   a.nacc = 512 / p->bn > 8 ? 8 : 512 / p->bn;
   if (pair && a.nacc > kEpiC) a.nacc = kEpiC;  // pair kernel: accumulator w is drained by epilogue warpgroup w
+  const char* env_own = getenv("HRV_CONV_EPI_OWN");  // A-B knob
+  a.epi_own = (!pair && !pixn && p->epi == HRV_EPI_LINEAR && a.nacc >= kEpiC && !(env_own && env_own[0] == '0')) ? 1 : 0;
+  if (a.epi_own) a.nacc = (a.nacc / kEpiC) * kEpiC;
   a.epi = p->epi; a.act = p->act;
   a.scale = p->scale; a.shift = p->shift;
   a.out = out.ptr; a.out_pitch = out.pitch; a.out_dtype = out.dtype; a.out_layout = p->out_layout; a.out_c = out.c;

@@ -411,9 +411,9 @@ def l1_sum(a, b):
     return out
 
 
-def l1_bwd(a, b, gscale, relu_gate=False):
-    """da = sign(a - b) * gscale (gscale: 1-element fp32 cuda tensor); relu_gate: times (a > 0)."""
-    da = Act.empty(a.n, a.h, a.w, a.c, pitch=a.pitch if a.c0 == 0 else None)
+def l1_bwd(a, b, gscale, relu_gate=False, out=None):
+    """da = sign(a - b) * gscale (gscale: 1-element fp32 cuda tensor); relu_gate: times (a > 0).  out: Act to write into."""
+    da = out if out is not None else Act.empty(a.n, a.h, a.w, a.c, pitch=a.pitch if a.c0 == 0 else None)
     ta, tb, td = a.ct(), b.ct(), da.ct()
     with _Timed("glue", 0.0, label="l1_bwd"):
         capi.check(_L(a).hrv_l1_bwd(ctypes.byref(ta), ctypes.byref(tb), gscale.data_ptr(), ctypes.byref(td), 1 if relu_gate else 0, _stream()), "l1_bwd")

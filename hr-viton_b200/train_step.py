@@ -222,14 +222,14 @@ class Stage2Trainer(_GraphMixin):
         # ---------------- generator update (train_generator.py:279-322)
         out = self.G(g_in, parse)
         d_in = torch.cat((torch.cat((parse, out), 1), torch.cat((parse, im), 1)), 0)
-        pred = autograd_g.discriminator_forward_train(self.D, d_in, need_wgrad=False, as_float=False)  # D grads are zeroed before use (:354)
-        pred_fake, pred_real = self._split(pred)
+        pred = autograd_g.discriminator_forward_train(self.D, d_in, need_wgrad=False, as_float=False, raw=True)  # D grads are zeroed before use (:354)
+        pred_fake, _ = self._split([[p[-1]] for p in pred])
         loss_gan = self.crit_gan(pred_fake, True, for_discriminator=False)
         loss_feat = 0
-        num_d = len(pred_fake)
+        num_d = len(pred)
         for i in range(num_d):
-            for j in range(len(pred_fake[i]) - 1):
-                loss_feat = loss_feat + (pred_fake[i][j] - pred_real[i][j].detach()).abs().mean(dtype=torch.float32) * self.lambda_feat / num_d
+            for j in range(len(pred[i]) - 1):  # intermediate features: [fake; real] halves of one pixel-major buffer
+                loss_feat = loss_feat + autograd_g.FeatMatchFn.apply(pred[i][j]) * self.lambda_feat / num_d
         loss_vgg = autograd_g.vgg_loss(self.vgg, self.vgg_weights, out, im) * self.lambda_vgg
         loss_gen = (loss_gan + loss_feat + loss_vgg).mean()
         self.opt_g.zero_grad(set_to_none=True)

@@ -1,7 +1,7 @@
 """GPU: gradient parity of the training path (hrviton_b200.autograd_g / autograd_tocg) against torch autograd run through the
 CPU oracle (fp32) on identical weights / inputs / noise.  Bounds are derived, not hand-picked: the same oracle is re-run with its
 convolutions rounding to bf16 (oracle.storage_rounding, gradients rounded at the same points) and the kernels' per-parameter
-relative L2 errors must stay within 1.1 x that floor in median / p90 (1.25 x in max; 1.6-2 x per individual parameter)."""
+relative L2 errors must stay within 1.1 x that floor in median / p90 (floors.RATIO_MAX in max; 1.6-2 x per individual parameter)."""
 import os
 import sys
 

@@ -575,3 +575,22 @@ def test_conv_pair_kernel_matches_single_cta_kernel(case):
     else:  # tap-by-tap K order in the one-CTA kernel: fp32 sums differ in the last bits -> at most one bf16 ulp of the largest output
         assert d <= 2 ** -7 * float(a.abs().max())
         assert ga is None or float((ga - gb).abs().max()) <= 2 ** -7 * float(ga.abs().max())
+
+
+def test_feature_matching_term_matches_torch():
+    """autograd_g.FeatMatchFn (hrv_l1_sum / hrv_l1_bwd over the [fake; real] halves of one discriminator feature buffer) against the
+    reference expression of train_generator.py:303-311, value and gradient (the real half gets exactly zero)."""
+    from hrviton_b200 import autograd_g
+    g = torch.Generator().manual_seed(5)
+    buf = torch.randn(6, 33, 25, 64, generator=g).to(torch.bfloat16).to(DEV).requires_grad_(True)
+    loss = autograd_g.FeatMatchFn.apply(buf) * 2.5
+    loss.backward()
+    ref_in = buf.detach().float().requires_grad_(True)
+    v = ref_in.permute(0, 3, 1, 2)
+    ref = (v[:3] - v[3:].detach()).abs().mean() * 2.5
+    ref.backward()
+    assert abs(float(loss) - float(ref)) < 1e-5 * abs(float(ref))
+    got, want = buf.grad.float(), ref_in.grad
+    assert float(got[3:].abs().max()) == 0.0
+    # sign(a-b) * 2.5 / numel, rounded to bf16 once
+    assert torch.allclose(got[:3], want[:3].to(torch.bfloat16).float(), rtol=0, atol=0)
