@@ -64,6 +64,7 @@ struct alignas(64) ConvArgs {
   int gamma_pitch;
   int pairs, tiles_m, store_c;  // pixel-N variant: 256-pixel tiles (pairs of 128-pixel boxes), channels written per pixel
   int epi_tab;                  // CTA-pair kernel, SPADE: per-warpgroup constant tables in shared memory
+  int tap_group;                // halo mainloops, 3x3: MMAs of a whole weight stage (9 taps, or one kernel row of 3) issued from one elected region
   int epi_own;                  // one-CTA kernel, LINEAR: accumulator i is drained by epilogue warpgroup i % kEpiC alone (whole tile)
   unsigned long long* stats;    // debug (tools/conv_stall_probe.py): per-CTA cycle counters of the warp roles, or nullptr
 };
@@ -388,6 +389,30 @@ __device__ __forceinline__ void epi_spade_tile(const ConvArgs& a, const EpiTile&
   }
 }
 
+// ------------------------------------------------------------------------------------------------ unrolled MMA issue of a tap group
+// The per-tap issue loop costs the MMA warp ~290 cycles per tap whatever the tile width: every iteration elects a lane, moves six
+// descriptor words from vector to uniform registers (R2UR; UTCHMMA takes uniform operands), re-reads its loop bound from the constant
+// bank (LDCU -> MOV -> ISETP -> BRA), reconverges (BSYNC / BRA.DIV).  For tiles of <= 64 columns that is 3-7x the tensor pipe's own
+// time for the tap (profiles/r2_conv_stall_thin_tiles_ab.txt: 2634 cycles per tile for 18 MMAs of 40 cycles).  Here ONE elected
+// region issues every MMA of a group of NT taps: the group's base descriptors cross to the uniform registers once, tap offsets inside
+// the group are compile-time constants of the 3x3 halo geometry (row pitch 8 + 3 - 1 = 10 pixels), and nothing is re-read.
+// NT = 9: all taps of a 3x3 kernel (weight stage holds 9 taps); NT = 3: one kernel row.
+template <int NT, int BKT, bool PAIR>
+__device__ __forceinline__ void issue_tap_group(uint32_t d_tmem, uint64_t da0, uint64_t db0, uint32_t b_step16, uint32_t idesc, uint32_t accumulate) {
+  constexpr uint32_t ROWB16 = (uint32_t)BKT * 2u / 16u;  // one pixel row of the halo tile, in descriptor units (16 B)
+#pragma unroll
+  for (int t = 0; t < NT; ++t) {
+    const uint32_t a_off = (uint32_t)((t / 3) * 10 + (t % 3)) * ROWB16;  // NT = 3: t / 3 == 0
+    const uint64_t da = da0 + a_off, db = db0 + (uint64_t)((uint32_t)t * b_step16);
+#pragma unroll
+    for (int kk = 0; kk < BKT / 16; ++kk) {
+      const uint32_t accf = (t == 0 && kk == 0) ? accumulate : 1u;
+      if (PAIR) umma_f16_2sm(d_tmem, da + 2u * kk, db + 2u * kk, idesc, accf);
+      else umma_f16(d_tmem, da + 2u * kk, db + 2u * kk, idesc, accf);
+    }
+  }
+}
+
 template <int BK>
 __global__ void __launch_bounds__(kThreadsC, 1) conv_igemm_kernel(const __grid_constant__ ConvArgs a) {
   constexpr uint32_t ROW_BYTES = BK * 2;               // one K chunk of one pixel / one output channel
@@ -549,6 +574,7 @@ __global__ void __launch_bounds__(kThreadsC, 1) conv_igemm_kernel(const __grid_c
       // descriptors = constant high words | (address >> 4); taps advance by adding row offsets
       const uint64_t da_hi = make_smem_desc(0, (uint32_t)a.line_pitch * ROW_BYTES, LAYOUT);  // SBO = one output row of 8 px
       const uint32_t row_wrap = (uint32_t)(a.line_pitch - a.KW) * ROW_BYTES;
+      const int group_mode = a.tap_group;  // 0 / 3 / 9 (host: 3x3, row pitch 10, tpb == group size)
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0, a_addr = stage0, b_addr = bstage0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -564,6 +590,17 @@ __global__ void __launch_bounds__(kThreadsC, 1) conv_igemm_kernel(const __grid_c
             mbar_wait_acct(bar_bfull(bs), bph, acct, w1);
             tc_fence_after();
             uint32_t sb_tap = b_addr;
+            if (group_mode) {  // 3x3: the whole group (9 taps, or one kernel row) from one elected region (issue_tap_group)
+              const uint64_t da0 = da_hi | (uint64_t)((sa_tap & 0x3FFFFu) >> 4);
+              const uint64_t db0 = db_hi | (uint64_t)((sb_tap & 0x3FFFFu) >> 4);
+              if (elect_one()) {
+                if (group_mode == 9) issue_tap_group<9, BK, false>(d_tmem, da0, db0, b_bytes >> 4, idesc, accumulate);
+                else issue_tap_group<3, BK, false>(d_tmem, da0, db0, b_bytes >> 4, idesc, accumulate);
+              }
+              __syncwarp();
+              accumulate = 1;
+              sa_tap += 10u * ROW_BYTES;  // next kernel row (unused after a 9-tap group)
+            } else
             for (int t = 0; t < a.tpb; ++t) {
               const uint64_t da = da_hi | (uint64_t)((sa_tap & 0x3FFFFu) >> 4);
               const uint64_t db = db_hi | (uint64_t)((sb_tap & 0x3FFFFu) >> 4);
@@ -809,6 +846,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsC, 1) conv_p
     const uint64_t db_hi = make_smem_desc(0, 8 * ROW_BYTES, LAYOUT);
     const uint64_t da_hi = make_smem_desc(0, (uint32_t)a.line_pitch * ROW_BYTES, LAYOUT);  // SBO = one output row of 8 px
     const uint32_t row_wrap = (uint32_t)(a.line_pitch - a.KW) * ROW_BYTES;
+    const int group_mode = a.tap_group;  // 0 / 3 / 9 (host: 3x3, row pitch 10, tpb == group size)
     uint32_t acc = 0, acc_ph = 0;
     int as = 0, bs = 0;
     uint32_t aph = 0, bph = 0, a_addr = stage0, b_addr = bstage0;
@@ -825,6 +863,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsC, 1) conv_p
           mbar_wait_acct(bar_bfull(bs), bph, acct, w1);
           tc_fence_after();
           uint32_t sb_tap = b_addr;
+          if (group_mode) {  // 3x3: the whole group (9 taps, or one kernel row) from one elected region (issue_tap_group)
+            const uint64_t da0 = da_hi | (uint64_t)((sa_tap & 0x3FFFFu) >> 4);
+            const uint64_t db0 = db_hi | (uint64_t)((sb_tap & 0x3FFFFu) >> 4);
+            if (elect_one()) {
+              if (group_mode == 9) issue_tap_group<9, BK, true>(d_tmem, da0, db0, b_bytes >> 4, idesc, accumulate);
+              else issue_tap_group<3, BK, true>(d_tmem, da0, db0, b_bytes >> 4, idesc, accumulate);
+            }
+            __syncwarp();
+            accumulate = 1;
+            sa_tap += 10u * ROW_BYTES;  // next kernel row (unused after a 9-tap group)
+          } else
           for (int t = 0; t < a.tpb; ++t) {
             const uint64_t da = da_hi | (uint64_t)((sa_tap & 0x3FFFFu) >> 4);
             const uint64_t db = db_hi | (uint64_t)((sb_tap & 0x3FFFFu) >> 4);
@@ -1356,6 +1405,8 @@ extern "C" int hrv_conv2d_fwd(const hrv_conv_params* p, hrv_stream stream) {
         if (taps % d == 0 && (uint32_t)d * b_rows * row_bytes <= tpb_cap && (uint32_t)sa * a.a_stage_bytes + (uint32_t)want * bs <= budget) { tpb = d; break; }
       }
     a.tpb = tpb;
+    const char* env_grp = getenv("HRV_CONV_TAP_GROUP");  // A-B knob
+    a.tap_group = (p->kh == 3 && p->kw == 3 && a.line_pitch == 10 && (tpb == 9 || tpb == 3) && !(env_grp && env_grp[0] == '0')) ? tpb : 0;
     a.b_stage_bytes = (int)(((uint32_t)tpb * b_rows * row_bytes + 1023u) & ~1023u);
     while (sa > 2 && (uint32_t)sa * a.a_stage_bytes + 2u * a.b_stage_bytes > budget) --sa;
     int sb = (int)((budget - (uint32_t)sa * a.a_stage_bytes) / (uint32_t)a.b_stage_bytes);
