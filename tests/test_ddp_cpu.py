@@ -111,3 +111,30 @@ def test_wrapper_keeps_module_attribute():
     assert w.module is m
     assert torch.equal(w(torch.ones(1, 2)), m(torch.ones(1, 2)))
     assert w.reduce_gradients() == 0  # no process group: pass-through
+
+
+def _buffers_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    bn = torch.nn.BatchNorm2d(3)
+    with torch.no_grad():
+        bn.running_mean.fill_(float(rank + 1))       # per-replica running statistics (what nn.BatchNorm2d under data parallelism gives)
+        bn.running_var.fill_(float(10 * (rank + 1)))
+        bn.num_batches_tracked.fill_(7 + rank)       # integer buffer: rank 0's value wins
+    ddp.average_module_buffers(bn)
+    out[rank] = (bn.running_mean.clone(), bn.running_var.clone(), int(bn.num_batches_tracked))
+    dist.destroy_process_group()
+
+
+def test_average_module_buffers_two_ranks():
+    """ddp.average_module_buffers: float buffers (BatchNorm running statistics) become the mean over ranks, integer buffers rank 0's —
+    the opt-in step before save_checkpoint for runs that want checkpoint statistics of the global batch (the reference's own semantics,
+    plain nn.BatchNorm2d under DataParallel, are per-replica statistics with replica 0's running buffers saved)."""
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_buffers_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    for r in range(world):
+        m, v, n = out[r]
+        assert torch.allclose(m, torch.full((3,), 1.5)) and torch.allclose(v, torch.full((3,), 15.0)) and n == 7

@@ -25,7 +25,8 @@ cases = [  # cin, n_gemm, k, h, w, spade
     (160, 160, 3, 1024, 768, False), (256, 256, 3, 256, 192, False), (512, 512, 3, 128, 96, False), (1040, 512, 3, 64, 48, False),
     (80, 160, 3, 1024, 768, False), (160, 128, 3, 1024, 768, False), (288, 128, 3, 512, 384, False), (128, 128, 3, 512, 384, False),
     (64, 64, 3, 1024, 768, False), (80, 32, 3, 1024, 768, False), (32, 32, 3, 1024, 768, False), (144, 64, 3, 512, 384, False),
-    (128, 128, 3, 512, 384, True), (32, 80, 3, 1024, 768, False)]
+    (128, 128, 3, 512, 384, True), (32, 80, 3, 1024, 768, False), (3, 64, 3, 1024, 768, False), (9, 16, 3, 1024, 768, False),
+    (64, 3, 3, 1024, 768, False), (3, 32, 3, 1024, 768, False)]
 if os.environ.get("HRV_PROBE_CASES"):  # e.g. "9,10,11,3"
     cases = [cases[int(i)] for i in os.environ["HRV_PROBE_CASES"].split(",")]
 os.environ.setdefault("HRV_CONV_PIXN", "0")  # default: probe the classic / pair kernels; HRV_CONV_PIXN=1 lets the dispatcher choose
