@@ -12,9 +12,13 @@
 //               128B/64B/32B swizzle on absolute shared-memory address bits (probed on B200: tools/umma_halo_probe.cu),
 //               exactly as TMA wrote it, so unaligned starts are legal.  KH*KW-fold less L2->smem traffic and TMA issue
 //               than tap-by-tap loading.  Weights ride a second ring with `tpb` taps per TMA (3-D box).
-//   Pipeline:   persistent CTAs (one per SM); warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
-//               warps 4.. = kEpiWG epilogue warpgroups (16-column chunks round-robin; loads issued before the TMEM read).  smem ring of `stages` (A,B) buffers with full/empty mbarriers; TMEM holds two
-//               accumulator buffers so the epilogue of tile i overlaps the MMAs of tile i+1.
+//   Pipeline:   persistent CTAs (one per SM); warp 0 = A (halo / tap) TMA producer, warp 3 = weight TMA producer of the halo
+//               mainloops, warp 1 = MMA issuer (issue_tap_group: one elected region per weight stage), warp 2 = TMEM allocator,
+//               warps 4.. = epilogue warpgroups (column split, or one whole tile per warpgroup: epi_own / pair kernel).  Rings of
+//               A and B stages with full/empty mbarriers; TMEM holds min(8, 512/BN) accumulators so epilogues overlap the MMAs.
+//   Kernels:    conv_igemm_kernel<BK> (one CTA, M = 128 pixels), conv_pair_kernel (2-CTA cluster, cta_group::2, M = 256 pixels,
+//               half of every weight stage per CTA), conv_pixn_kernel (weights as M, 256 pixels as N); hrv_conv2d_fwd picks one
+//               per layer from a measured table (profiles/r2_kernel_selection_ab.txt).
 //   Epilogues:  LINEAR  out = act(acc*scale + shift (+ residual))      (bias / folded BatchNorm / residual / tanh)
 //               SPADE   out = act((x + noise*ns - mean)*rstd*(1+gamma) + beta), gamma/beta = interleaved GEMM columns:
 //                       the SPADE modulation never leaves registers (network_generator.py:115-121,170-171).
@@ -986,9 +990,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsC, 1) conv_p
 }
 
 // ------------------------------------------------------------------------------------------------ pixel-N variant
-// tcgen05.mma (both operands in shared memory) costs ~153 cycles per K=16 instruction on B200 whatever M and N are
-// (tools/umma_rate_probe.cu, profiles/r1_umma_rate_probe.txt), so a convolution with few output channels wastes the tensor pipe
-// when the channels are the MMA's N.  This variant swaps the roles for Cout <= 128:
+// An M128 x N x K16 tcgen05.mma takes max(N/2, 32 + N/4) cycles (tools/umma_rate_probe.cu v2, profiles/r2_umma_rate_probe.txt; the
+// round-1 "153 cycles whatever N" was that probe's own scalar loop): few output channels as the MMA's N run the pipe at 20-66 %,
+// and every pixel tile re-reads the whole weight stage from shared memory.  This variant swaps the roles for Cout <= 128 — 256
+// pixels per instruction share one weight stage:
 //   A operand (M = 128 rows) = the packed weights (rows >= n_pad are TMA zero fill), B operand (N = 256) = 256 output pixels
 //   (two 128-pixel TMA boxes back to back), D[cout][pixel] in TMEM (2 x 256 columns).  Per instruction twice the pixels.
 // The epilogue thread owns one output channel (a TMEM lane): scale/shift/activation per thread, then a bf16 transpose through
