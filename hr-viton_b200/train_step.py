@@ -15,7 +15,8 @@ OCCLUSION_CLASSES = [1, 2, 5, 6, 7, 8, 9, 10, 11, 12]  # remove_overlap: seg_out
 
 def gaussian_blur_15_3(x):
     """tgm.image.GaussianBlur((15,15),(3,3)) restated: depth-wise separable 15-tap Gaussian, sigma 3, zero padding 7
-    (torchgeometry is absent; parity of this glue op is unpinned)."""
+    (torchgeometry is absent from the image; the restatement is pinned against scipy.ndimage.gaussian_filter, an
+    independent implementation of the same published filter: tests/test_host_logic.py)."""
     k = torch.arange(15, dtype=torch.float32, device=x.device) - 7
     g = torch.exp(-(k * k) / (2 * 3.0 * 3.0))
     g = g / g.sum()

@@ -138,3 +138,26 @@ def test_gaussian_blur_restatement_is_normalised_and_separable():
     z = torch.randn(1, 1, 32, 32, generator=torch.Generator().manual_seed(1))
     ref = F.conv2d(z, torch.outer(g, g)[None, None], padding=7)
     assert float((train_step.gaussian_blur_15_3(z) - ref).abs().max()) < 1e-5
+
+
+def test_gaussian_blur_restatement_matches_scipy_gaussian_filter():
+    """Independent pin of the one glue op whose reference implementation (torchgeometry 0.1.2, `tgm.image.GaussianBlur((15,15),(3,3))`,
+    train_generator.py:181 / test_generator.py:91) is absent from this image: its published algorithm is a normalised sampled
+    Gaussian exp(-x^2 / 2 sigma^2) of 15 taps applied separably with zero padding.  scipy.ndimage.gaussian_filter with
+    truncate = 7/3 (radius int(truncate*sigma + 0.5) = 7), mode='constant', cval=0 is the same filter written by someone else."""
+    import numpy as np
+    import scipy.ndimage as ndi
+    from hrviton_b200 import train_step
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((2, 3, 37, 29)).astype(np.float32)
+    ours = train_step.gaussian_blur_15_3(torch.from_numpy(x)).numpy()
+    want = np.stack([np.stack([ndi.gaussian_filter(x[n, c].astype(np.float64), sigma=3.0, truncate=7.0 / 3.0 + 1e-9, mode="constant", cval=0.0)
+                               for c in range(3)]) for n in range(2)])
+    assert ours.shape == want.shape
+    assert float(np.abs(ours - want).max()) < 2e-6
+    # the shim the reference scripts import resolves to the same filter on CPU tensors
+    import hrv_env
+    hrv_env.install()
+    import torchgeometry as tgm
+    shim = tgm.image.GaussianBlur((15, 15), (3, 3))(torch.from_numpy(x)).numpy()
+    assert float(np.abs(shim - want).max()) < 2e-6
